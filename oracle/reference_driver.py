@@ -1,0 +1,115 @@
+"""Drive the UNMODIFIED reference (meuleman/epilogos, /root/reference) on small inputs.
+
+TEST INFRASTRUCTURE ONLY.  This file is the only place that imports the reference.  It exists to
+(1) generate the golden fixtures committed under tests/golden/ (see tests/golden/make_golden.py) and
+(2) cross-check the numpy restatement in oracle/epilogos_oracle.py while authoring.
+/root/reference does not exist on the GPU box, so nothing in tests/, bench.py or smoke() imports this
+module at run time; they use the committed fixtures.
+
+The reference cannot be imported as-is in this image: helpers.py:7 pulls in filter_regions.py which
+imports natsort/pyranges (filter_regions.py:10), and run.py:14 pulls matplotlib/statsmodels.  None of
+those modules is touched by the hot path (expected.py, expectedCombination.py, scores.py), so empty
+stand-ins are registered in sys.modules before the import.
+"""
+import sys
+import types
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+REFERENCE_ROOT = Path("/root/reference")
+
+_STUBS = ["natsort", "pyranges", "matplotlib", "matplotlib.pyplot", "matplotlib.lines", "statsmodels",
+          "statsmodels.stats", "statsmodels.stats.multitest", "pysam"]
+
+
+def available():
+    return (REFERENCE_ROOT / "epilogos" / "scores.py").is_file()
+
+
+def _import_reference():
+    for name in _STUBS:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["statsmodels.stats.multitest"].multipletests = None
+    sys.modules["matplotlib.lines"].Line2D = None
+    if str(REFERENCE_ROOT) not in sys.path:
+        sys.path.insert(0, str(REFERENCE_ROOT))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos.expected import main as expected_main                      # expected.py:11
+        from epilogos.expectedCombination import main as combination_main        # expectedCombination.py:9
+        from epilogos.scores import main as scores_main                          # scores.py:14
+    return expected_main, combination_main, scores_main
+
+
+def write_matrix_tsv(path, states1, chrom="chr1", bin_size=200, start_bin=0):
+    """Write a 1-based state matrix in the reference's input format (README.md:286-292)."""
+    states1 = np.asarray(states1)
+    with open(path, "w") as f:
+        for r in range(states1.shape[0]):
+            lo = (start_bin + r) * bin_size
+            f.write("%s\t%d\t%d\t" % (chrom, lo, lo + bin_size))
+            f.write("\t".join(str(int(v)) for v in states1[r]))
+            f.write("\n")
+
+
+def run_single(states0, num_states, saliency, nproc=1, chrom="chr1"):
+    """states0: 0-based [bins, C].  Returns dict(counts=int64 table, exp=float32 table, scores=f32 [bins,K],
+    scores_text=bytes of the decompressed scores_*.txt.gz)."""
+    import gzip
+    expected_main, combination_main, scores_main = _import_reference()
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        inp = d / "in"
+        out = d / "out"
+        inp.mkdir(); out.mkdir()
+        f = inp / ("epilogos_matrix_%s.txt" % chrom)
+        write_matrix_tsv(f, np.asarray(states0) + 1, chrom=chrom)
+        tag = "in_s%d" % saliency
+        expected_main(f, "null", num_states, saliency, out, tag, nproc, False)
+        tmp = out / ("temp_exp_freq_%s_%s.npy" % (tag, f.name.split(".")[0]))
+        counts = np.load(tmp)
+        exp_path = out / ("exp_freq_%s.npy" % tag)
+        combination_main(out, exp_path, tag, False)
+        exp = np.load(exp_path)
+        scores_main(f, "null", num_states, saliency, out, exp_path, tag, nproc, num_states - 1, -1, False)
+        npz = np.load(out / ("temp_scores_%s_%s.npz" % (tag, f.name.split(".")[0])), allow_pickle=True)
+        with gzip.open(out / ("scores_%s_%s.txt.gz" % (tag, f.name.split(".")[0])), "rb") as g:
+            text = g.read()
+        return dict(counts=counts, exp=exp, scores=np.array(npz["scoreArr"]), scores_text=text)
+
+
+def run_paired(statesA0, statesB0, num_states, saliency, seed, quiescent_state=None, group_size=-1, nproc=1,
+               chrom="chr1"):
+    """Paired mode with a seeded parent RNG (np.random.seed(seed) before scores.main makes the unseeded
+    shuffle of helpers.py:183-184 reproducible)."""
+    import gzip
+    expected_main, combination_main, scores_main = _import_reference()
+    if quiescent_state is None:
+        quiescent_state = num_states - 1
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        a = d / "a"; b = d / "b"; out = d / "out"
+        a.mkdir(); b.mkdir(); out.mkdir()
+        fa = a / ("epilogos_matrix_%s.txt" % chrom)
+        fb = b / ("epilogos_matrix_%s.txt" % chrom)
+        write_matrix_tsv(fa, np.asarray(statesA0) + 1, chrom=chrom)
+        write_matrix_tsv(fb, np.asarray(statesB0) + 1, chrom=chrom)
+        tag = "a_b_s%d" % saliency
+        stem = fa.name.split(".")[0]
+        expected_main(fa, fb, num_states, saliency, out, tag, nproc, False)
+        counts = np.load(out / ("temp_exp_freq_%s_%s.npy" % (tag, stem)))
+        exp_path = out / ("exp_freq_%s.npy" % tag)
+        combination_main(out, exp_path, tag, False)
+        exp = np.load(exp_path)
+        np.random.seed(seed)
+        scores_main(fa, fb, num_states, saliency, out, exp_path, tag, nproc, quiescent_state, group_size, False)
+        null = np.load(out / ("temp_nullDistances_%s_%s.npz" % (tag, stem)))["nullDistances"]
+        quies = np.load(out / ("temp_quiescence_%s_%s.npz" % (tag, stem)))["quiescenceArr"]
+        with gzip.open(out / ("pairwiseDelta_%s_%s.txt.gz" % (tag, stem)), "rb") as g:
+            text = g.read()
+        return dict(counts=counts, exp=exp, null_distances=np.array(null), quiescence=np.array(quies),
+                    delta_text=text)

@@ -1,0 +1,122 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run once in the authoring container (needs /root/reference):   python tests/golden/make_golden.py
+The reference ships no tests / golden vectors for the scoring path, so the goldens
+are outputs of the reference itself (expected.main -> expectedCombination.main -> scores.main through
+oracle/reference_driver.py) on
+  * a real-data slice: 10 biosamples x 4000 bins of chr1 built from /root/reference/data/ChromHMM with the
+    paste recipe of bin/preprocess_data_ChromHMM.sh:34-49 (rows 100000..103999, a varied region), and
+  * small seeded synthetic matrices of the benchmark shapes (C=833/K=18, C=127/K=15).
+Each fixture is a compressed .npz holding the 0-based int8 input and the reference outputs.
+"""
+import gzip
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent.parent))
+
+from oracle import reference_driver as ref            # noqa: E402
+from oracle import epilogos_oracle as orc              # noqa: E402
+
+
+def real_slice(lo=100000, n=4000):
+    files = sorted((ref.REFERENCE_ROOT / "data" / "ChromHMM").glob("*_chr1_statebyline.txt.gz"))
+    cols = []
+    for f in files:
+        with gzip.open(f, "rt") as g:
+            lines = g.read().split("\n")
+        vals = np.array([int(v) for v in lines[2:2 + lo + n] if v != ""][lo:lo + n], dtype=np.int8)
+        cols.append(vals)
+    return np.stack(cols, axis=1) - 1
+
+
+def text_digest(text):
+    return np.frombuffer(hashlib.sha256(text).digest(), dtype=np.uint8)
+
+
+def single_case(name, x, k, saliencies, keep_text=True, nproc=1):
+    out = {"x": x.astype(np.int8), "num_states": np.int64(k)}
+    for s in saliencies:
+        r = ref.run_single(x, k, s, nproc=nproc)
+        out["s%d_counts" % s] = r["counts"]
+        out["s%d_exp" % s] = r["exp"]
+        out["s%d_scores" % s] = r["scores"]
+        out["s%d_text_sha256" % s] = text_digest(r["scores_text"])
+        if keep_text:
+            out["s%d_text" % s] = np.frombuffer(r["scores_text"], dtype=np.uint8)
+    np.savez_compressed(HERE / (name + ".npz"), **out)
+    print("wrote", name, {k_: getattr(v, "shape", None) for k_, v in out.items()})
+
+
+def paired_case(name, xa, xb, k, saliencies, seed, group_size=-1, quiescent_state=None):
+    out = {"xa": xa.astype(np.int8), "xb": xb.astype(np.int8), "num_states": np.int64(k),
+           "seed": np.int64(seed), "group_size": np.int64(group_size),
+           "quiescent_state": np.int64(k - 1 if quiescent_state is None else quiescent_state)}
+    for s in saliencies:
+        r = ref.run_paired(xa, xb, k, s, seed, quiescent_state=quiescent_state, group_size=group_size)
+        out["s%d_counts" % s] = r["counts"]
+        out["s%d_exp" % s] = r["exp"]
+        out["s%d_null" % s] = r["null_distances"]
+        out["s%d_quiescence" % s] = r["quiescence"]
+        out["s%d_delta_text" % s] = np.frombuffer(r["delta_text"], dtype=np.uint8)
+    np.savez_compressed(HERE / (name + ".npz"), **out)
+    print("wrote", name)
+
+
+def s3_big_case(name, bins=48, cols=833, k=18, seed=11):
+    """S3 at the benchmark width.  The 0.9 GB tables cannot be committed: keep sha256 digests of the
+    int64 count table and float32 expected table, a strided sample of entries, and the reference scores."""
+    x = orc.synth_states(bins, cols, k, seed)
+    r = ref.run_single(x, k, 3)
+    counts, exp = r["counts"], r["exp"]
+    flat_idx = np.arange(0, counts.size, 100003, dtype=np.int64)
+    out = {"x": x.astype(np.int8), "num_states": np.int64(k),
+           "counts_sha256": np.frombuffer(hashlib.sha256(np.ascontiguousarray(counts).tobytes()).digest(), np.uint8),
+           "exp_sha256": np.frombuffer(hashlib.sha256(np.ascontiguousarray(exp).tobytes()).digest(), np.uint8),
+           "sample_idx": flat_idx, "counts_sample": counts.ravel()[flat_idx], "exp_sample": exp.ravel()[flat_idx],
+           "s3_scores": r["scores"], "counts_dtype": np.array(str(counts.dtype))}
+    np.savez_compressed(HERE / (name + ".npz"), **out)
+    print("wrote", name)
+
+
+def main():
+    which = set(sys.argv[1:])
+
+    def want(n):
+        return not which or n in which
+
+    real = real_slice()
+    if want("real10"):
+        single_case("real10_chr1_k18", real, 18, (1, 2, 3))
+    if want("real10_mp"):
+        # three worker processes: exercises splitRows chunking (helpers.py:102-120); results must not change
+        single_case("real10_chr1_k18_nproc3", real[:1000], 18, (1, 2), keep_text=False, nproc=3)
+    if want("synth833"):
+        single_case("synth_c833_k18", orc.synth_states(1500, 833, 18, seed=1), 18, (1, 2), keep_text=False)
+    if want("synth833u"):
+        single_case("synth_uniform_c833_k18", orc.synth_states(600, 833, 18, seed=2, kind="uniform"), 18, (1, 2),
+                    keep_text=False)
+    if want("synth127"):
+        single_case("synth_c127_k15", orc.synth_states(2000, 127, 15, seed=3), 15, (1, 2), keep_text=False)
+    if want("s3small"):
+        single_case("synth_s3_c12_k15", orc.synth_states(300, 12, 15, seed=4, kind="uniform"), 15, (3,),
+                    keep_text=False)
+        single_case("synth_s3_c40_k18", orc.synth_states(500, 40, 18, seed=5), 18, (3,), keep_text=False)
+    if want("paired_real"):
+        paired_case("paired_real10_k18", real[:, :5], real[:, 5:], 18, (1, 2), seed=7)
+    if want("paired_synth"):
+        xa = orc.synth_states(1200, 30, 18, seed=8)
+        xb = orc.synth_states(1200, 25, 18, seed=9)
+        paired_case("paired_synth_c30_c25_k18", xa, xb, 18, (1, 2), seed=10)
+        paired_case("paired_synth_g20_k18", xa, xb, 18, (1, 2), seed=12, group_size=20)
+        paired_case("paired_synth_q0_k18", xa[:400], xb[:400], 18, (1,), seed=13, quiescent_state=-1)
+    if want("s3big"):
+        s3_big_case("synth_s3_c833_k18")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""Pin the CPU oracle (oracle/epilogos_oracle.py) to outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by tests/golden/make_golden.py, which runs
+expected.main -> expectedCombination.main -> scores.main of /root/reference.  Integer tables and the
+float32 expected payload must match bit-for-bit; float32 scores must match bit-for-bit as well (the
+oracle uses the same numpy ufuncs as the reference), and the formatted text byte-for-byte.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import epilogos_oracle as orc
+
+SINGLE = ["real10_chr1_k18", "real10_chr1_k18_nproc3", "synth_c833_k18", "synth_uniform_c833_k18", "synth_c127_k15"]
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_s1_s2_tables_and_scores_match_reference(golden, name):
+    g = golden(name)
+    x, k = g["x"], int(g["num_states"])
+    n1 = orc.s1_expected_counts(x, k)
+    n2 = orc.s2_expected_counts(x, k)
+    assert n1.dtype == g["s1_counts"].dtype and np.array_equal(n1, g["s1_counts"])
+    assert n2.dtype == g["s2_counts"].dtype and np.array_equal(n2, g["s2_counts"])
+    e1, e2 = orc.normalize_expected(n1), orc.normalize_expected(n2)
+    assert e1.tobytes() == g["s1_exp"].tobytes()
+    assert e2.tobytes() == g["s2_exp"].tobytes()
+    assert orc.s1_scores(x, k, e1).tobytes() == g["s1_scores"].tobytes()
+    assert orc.s2_scores(x, k, e2).tobytes() == g["s2_scores"].tobytes()
+
+
+@pytest.mark.parametrize("name", ["real10_chr1_k18", "synth_c127_k15"])
+def test_rowloop_port_equals_vectorised(golden, name):
+    g = golden(name)
+    x, k = g["x"][:300], int(g["num_states"])
+    assert np.array_equal(orc.s1_expected_counts_rowloop(x, k), orc.s1_expected_counts(x, k))
+    assert np.array_equal(orc.s2_expected_counts_rowloop(x, k), orc.s2_expected_counts(x, k))
+    e1, e2 = g["s1_exp"], g["s2_exp"]
+    assert orc.s1_scores_rowloop(x, k, e1).tobytes() == orc.s1_scores(x, k, e1).tobytes()
+    assert orc.s2_scores_rowloop(x, k, e2).tobytes() == orc.s2_scores(x, k, e2).tobytes()
+
+
+def test_scores_text_matches_reference_bytes(golden):
+    g = golden("real10_chr1_k18")
+    bins = g["x"].shape[0]
+    # make_golden writes the slice with start_bin=0 (reference_driver.write_matrix_tsv)
+    starts = np.arange(bins) * 200
+    for s in (1, 2, 3):
+        text = orc.format_scores_text(g["s%d_scores" % s], "chr1", starts, starts + 200)
+        assert text == g["s%d_text" % s].tobytes()
+        assert hashlib.sha256(text).digest() == g["s%d_text_sha256" % s].tobytes()
+
+
+@pytest.mark.parametrize("name", ["real10_chr1_k18", "synth_s3_c12_k15", "synth_s3_c40_k18"])
+def test_s3_tables_and_scores_match_reference(golden, name):
+    g = golden(name)
+    x, k = g["x"], int(g["num_states"])
+    n3 = orc.s3_expected_counts(x, k)
+    assert n3.dtype == g["s3_counts"].dtype and np.array_equal(n3, g["s3_counts"])
+    c = x.shape[1]
+    assert int(n3.sum()) == x.shape[0] * c * (c - 1)
+    assert not n3[np.arange(c), np.arange(c)].any()
+    assert np.array_equal(n3, n3.transpose(1, 0, 3, 2))
+    e3 = orc.normalize_expected(n3)
+    assert e3.tobytes() == g["s3_exp"].tobytes()
+    sub = slice(0, 200)
+    ref32 = orc.s3_scores_rowloop(x[sub], k, e3)
+    assert ref32.tobytes() == g["s3_scores"][sub].tobytes()
+    # the exact-arithmetic variant agrees with the reference's float32 to its accumulation noise
+    f64 = orc.s3_scores_f64(x[sub], k, e3)
+    assert np.max(np.abs(f64 - ref32)) < 2e-2
+    assert np.array_equal(orc.s3_expected_counts_rowloop(x[:50], k), orc.s3_expected_counts(x[:50], k))
+
+
+PAIRED = ["paired_real10_k18", "paired_synth_c30_c25_k18", "paired_synth_g20_k18", "paired_synth_q0_k18"]
+
+
+@pytest.mark.parametrize("name", PAIRED)
+def test_paired_matches_reference(golden, name):
+    g = golden(name)
+    xa, xb, k = g["xa"], g["xb"], int(g["num_states"])
+    seed, gs, q = int(g["seed"]), int(g["group_size"]), int(g["quiescent_state"])
+    comb = np.concatenate((xa, xb), axis=1)
+    perm = orc.reference_shuffle_indices(seed, comb.shape[0], comb.shape[1])
+    bins = xa.shape[0]
+    starts = np.arange(bins) * 200
+    for s in (1, 2):
+        if "s%d_counts" % s not in g.files:
+            continue
+        counts = orc.s1_expected_counts(comb, k) if s == 1 else orc.s2_expected_counts(comb, k)
+        assert np.array_equal(counts, g["s%d_counts" % s])
+        exp = orc.normalize_expected(counts)
+        assert exp.tobytes() == g["s%d_exp" % s].tobytes()
+        r = orc.paired_scores(xa, xb, perm, k, s, exp, q, gs)
+        assert np.array_equal(r["quiescence"], g["s%d_quiescence" % s])
+        assert r["null_distances"].dtype == np.float32
+        assert r["null_distances"].tobytes() == g["s%d_null" % s].tobytes()
+        text = orc.format_scores_text(r["delta"], "chr1", starts, starts + 200)
+        assert text == g["s%d_delta_text" % s].tobytes()
+
+
+def test_kl_masks():
+    obs = np.array([0.0, 0.5, 0.25, 0.0])
+    exp = np.array([0.5, 0.0, 0.25, 0.0], dtype=np.float32)
+    out = orc.kl_terms(obs, exp)
+    assert out.dtype == np.float64 and np.array_equal(out, np.zeros(4))
+    assert orc.kl_terms(np.float32([0.5]), np.float32([0.25])).dtype == np.float32
+
+
+def test_synth_generator_is_seeded():
+    a = orc.synth_states(64, 33, 18, seed=5)
+    b = orc.synth_states(64, 33, 18, seed=5)
+    assert a.dtype == np.int8 and np.array_equal(a, b) and a.min() >= 0 and a.max() < 18
