@@ -1,0 +1,142 @@
+"""Thin torch-tensor wrappers over the C ABI (include/epilogos_b200.h).
+
+torch is used for device memory, streams and (in the stage drivers) torch.distributed only; every
+computation below is a call into libepilogos_b200.so.  All functions raise if the library or a B200 is
+missing -- there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_SCORE_DIRECT, EPI_SCORE_TABLE  # noqa: F401
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+
+
+def pitch_for(cols):
+    """Row pitch (bytes) of the packed state matrix: next multiple of 16 (TMA global stride rule)."""
+    return (int(cols) + 15) & ~15
+
+
+def pack_states(states0, pin=True):
+    """0-based integer state matrix [bins, C] (any int dtype, numpy) -> pinned int8 [bins, pitch] torch tensor.
+    Mirrors the tail of helpers.readStates (helpers.py:154-155: labels - 1, here narrowed to int8).
+    Pad bytes are zero and never interpreted."""
+    a = np.asarray(states0)
+    if a.ndim != 2:
+        raise ValueError("state matrix must be 2-D [bins, biosamples]")
+    if a.size and (a.min() < 0 or a.max() >= _lib.EPI_MAX_STATES):
+        raise ValueError("state labels must be in [0, %d)" % _lib.EPI_MAX_STATES)
+    bins, cols = a.shape
+    out = torch.zeros((bins, pitch_for(cols)), dtype=torch.int8, pin_memory=bool(pin and torch.cuda.is_available()))
+    out.numpy()[:, :cols] = a
+    return out
+
+
+def bin_counts(x, cols, num_states, out=None):
+    """K1.  x: CUDA int8 [bins, pitch]; returns CUDA int16 tensor [bins, K] holding uint16 counts."""
+    _require_cuda(x, torch.int8, "x")
+    bins, pitch = x.shape
+    if out is None:
+        out = torch.empty((bins, num_states), dtype=torch.int16, device=x.device)
+    _lib.call("epi_bin_counts", _ptr(x), bins, int(cols), pitch, int(num_states), _ptr(out), _stream())
+    return out
+
+
+def expected_tables(cnt, width, want_s1=True, want_s2=True):
+    """K2.  Returns (n1 int64[K] or None, n2 int64[K,K] or None) for this shard."""
+    _require_cuda(cnt, torch.int16, "cnt")
+    bins, k = cnt.shape
+    n1 = torch.zeros(k, dtype=torch.int64, device=cnt.device) if want_s1 else None
+    n2 = torch.zeros((k, k), dtype=torch.int64, device=cnt.device) if want_s2 else None
+    _lib.call("epi_expected_s1s2", _ptr(cnt), bins, k, int(width), _ptr(n1), _ptr(n2), _stream())
+    return n1, n2
+
+
+def normalize(counts):
+    """K4.  int64 count table -> float32 probabilities (expectedCombination.py:42)."""
+    _require_cuda(counts, torch.int64, "counts")
+    out = torch.empty(counts.shape, dtype=torch.float32, device=counts.device)
+    _lib.call("epi_normalize_i64", _ptr(counts), counts.numel(), _ptr(out), _stream())
+    return out
+
+
+def scores_s1(cnt, width, exp1, want64=False, mode=EPI_SCORE_TABLE, out32=None):
+    _require_cuda(cnt, torch.int16, "cnt")
+    _require_cuda(exp1, torch.float32, "exp1")
+    bins, k = cnt.shape
+    if exp1.numel() != k:
+        raise ValueError("expected table has %d entries, need %d" % (exp1.numel(), k))
+    if out32 is None:
+        out32 = torch.empty((bins, k), dtype=torch.float32, device=cnt.device)
+    out64 = torch.empty((bins, k), dtype=torch.float64, device=cnt.device) if want64 else None
+    _lib.call("epi_scores_s1", _ptr(cnt), bins, k, int(width), _ptr(exp1), _ptr(out32), _ptr(out64), int(mode),
+              _stream())
+    return (out32, out64) if want64 else out32
+
+
+def scores_s2(cnt, width, exp2, perms=None, want64=False, mode=EPI_SCORE_TABLE, out32=None):
+    _require_cuda(cnt, torch.int16, "cnt")
+    _require_cuda(exp2, torch.float32, "exp2")
+    bins, k = cnt.shape
+    if exp2.numel() != k * k:
+        raise ValueError("expected table has %d entries, need %d" % (exp2.numel(), k * k))
+    if perms is None:
+        perms = int(width) * (int(width) - 1)
+    if out32 is None:
+        out32 = torch.empty((bins, k), dtype=torch.float32, device=cnt.device)
+    out64 = torch.empty((bins, k), dtype=torch.float64, device=cnt.device) if want64 else None
+    _lib.call("epi_scores_s2", _ptr(cnt), bins, k, int(width), int(perms), _ptr(exp2), _ptr(out32), _ptr(out64),
+              int(mode), _stream())
+    return (out32, out64) if want64 else out32
+
+
+def single_host(x_host, cols, num_states, saliency, want_scores=True):
+    """Whole S1/S2 path on a HOST matrix (numpy int8 [bins, pitch] or a pinned torch int8 tensor).
+    Returns (counts int64 ndarray, exp float32 ndarray, scores float32 ndarray or None)."""
+    if isinstance(x_host, torch.Tensor):
+        if x_host.is_cuda or x_host.dtype != torch.int8 or not x_host.is_contiguous():
+            raise TypeError("x_host must be a contiguous CPU int8 tensor")
+        bins, pitch = x_host.shape
+        xp = ctypes.c_void_p(x_host.data_ptr())
+    else:
+        x_host = np.ascontiguousarray(x_host, dtype=np.int8)
+        bins, pitch = x_host.shape
+        xp = ctypes.c_void_p(x_host.ctypes.data)
+    shape = (num_states,) if saliency == 1 else (num_states, num_states)
+    counts = np.empty(shape, dtype=np.int64)
+    exp = np.empty(shape, dtype=np.float32)
+    scores = None
+    sp = ctypes.c_void_p(0)
+    if want_scores:
+        scores_t = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
+        scores = scores_t.numpy()
+        sp = ctypes.c_void_p(scores_t.data_ptr())
+        single_host._keep = scores_t
+    _lib.call("epi_single_host", xp, bins, int(cols), pitch, int(num_states), int(saliency),
+              ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(exp.ctypes.data), sp)
+    return counts, exp, scores
+
+
+def device_info():
+    sm, major, minor = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.call("epi_device_info", ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
+    return dict(sm_count=sm.value, cc=(major.value, minor.value))
+
+
+def counts_to_numpy(cnt):
+    """CUDA int16 storage of uint16 counts -> numpy uint16."""
+    return cnt.cpu().numpy().view(np.uint16)

@@ -1,0 +1,89 @@
+/*
+ * epilogos_b200 -- C ABI of the B200 (sm_100a) implementation of the Epilogos scoring hot path.
+ *
+ * This header is the drop-in boundary.  The reference (meuleman/epilogos, pure Python) has no FFI; the
+ * entry points below are what a binding for its hot functions would call, one per reference function
+ * (file:line cited on each).  Signatures use plain pointers and sizes only -- no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; epi_last_error() returns a message for
+ *     the calling thread (the Python layer raises RuntimeError with it; the reference raises Python
+ *     exceptions and has no error codes).
+ *   - "device pointer" = memory of the current CUDA device (cudaMalloc / torch tensor .data_ptr()).
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-level entry
+ *     points are asynchronous on that stream; *_host entry points take host pointers, do their own
+ *     H2D/D2H copies and return after the results are in the host buffers.
+ *   - the state matrix is int8, 0-based (label - 1, helpers.py:154-155), bins x biosamples, row pitch in
+ *     bytes.  The fast path wants pitch % 16 == 0 and a 16-byte aligned base (the packer produces that);
+ *     any other pitch is repacked on the device first.  Pad bytes are never interpreted.
+ *     Labels must be < num_states (the packer validates; the reference would raise IndexError).
+ *   - per-bin state counts are uint16 [bins][num_states] (a count is <= biosamples <= 65535).
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef EPILOGOS_B200_H
+#define EPILOGOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPI_ABI_VERSION 1
+#define EPI_MAX_STATES 32
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int epi_abi_version(void);
+const char* epi_last_error(void);
+/* sm count, compute capability of the current device; fails when there is no CUDA device. */
+int epi_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: per-bin state counts ----------------------------------------------------------------
+ * cnt[b][s] = #{ j < cols : x[b][j] == s }.
+ * Replaces np.unique(dataArr[row], return_counts=True) in expected.py:111,152 and scores.py:341,444. */
+int epi_bin_counts(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
+                   uint16_t* cnt_dev, void* stream);
+
+/* ---- K2: S1 / S2 expected count tables from the per-bin counts -------------------------------
+ * n1[s]    += sum_b cnt[b][s]                                   (expected.py:106-113, s1Calc)
+ * n2[s][t] += sum_b cnt[b][s]*cnt[b][t] - [s==t]*cnt[b][s]      (expected.py:146-158, s2Calc)
+ * Accumulates into int64 device arrays (caller zeroes them); either pointer may be NULL.
+ * `width` = biosamples per row (upper bound of a count). */
+int epi_expected_s1s2(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width,
+                      int64_t* n1_dev, int64_t* n2_dev, void* stream);
+
+/* ---- K4: normalise an int64 count table -------------------------------------------------------
+ * out[i] = (float)((double)counts[i] / (double)sum(counts))     (expectedCombination.py:42) */
+int epi_normalize_i64(const int64_t* counts_dev, int64_t n, float* out_dev, void* stream);
+
+/* ---- K5: S1 / S2 scores from the per-bin counts -----------------------------------------------
+ * S1: score[b][s] = o*log2(o/E1[s]), o = cnt[b][s]/width        (scores.py:339-344, 317, 550)
+ * S2: score[b][t] = sum_s o_st*log2(o_st/E2[s][t]) added in order s = 0..K-1,
+ *     o_st = (cnt_s*cnt_t - [s==t]cnt_s)/perms                  (scores.py:443-451, 412, 550)
+ *     `width` = biosamples per row (upper bound of a count); `perms` = C*(C-1) of the group the
+ *     observation is normalised with (they differ only for the -g quirk of scores.py:397-398).
+ * Terms with o == 0 or E == 0 are 0 (numpy.ma masking of klScoreND).
+ * out32 (float32, the reference's stored dtype) and/or out64 (unrounded float64) may be NULL.
+ * mode: EPI_SCORE_TABLE evaluates log2 through tables of log2(count) and log2(E) (default, within
+ *       1e-9 relative + 1e-12 absolute of the float64 reference); EPI_SCORE_DIRECT evaluates
+ *       obs*log2(obs/E) term by term with a correctly rounded divide (verification path). */
+#define EPI_SCORE_TABLE 0
+#define EPI_SCORE_DIRECT 1
+int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width,
+                  const float* exp1_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream);
+int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width, int64_t perms,
+                  const float* exp2_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream);
+
+/* ---- whole path with HOST buffers (what expected.main -> expectedCombination.main -> scores.main
+ *      compute for one in-memory matrix; run.py:196,231,246) ------------------------------------
+ * x_host: int8 [bins][pitch] (any pitch >= cols; pinned memory makes the copies asynchronous).
+ * saliency 1 or 2.  counts_host: int64 [K] or [K*K] (the temp_exp_freq payload), exp_host: float32
+ * same shape (the exp_freq payload), scores_host: float32 [bins][K].  Any output may be NULL.
+ * H2D of the matrix is chunked and overlapped with the count kernel. */
+int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
+                    int32_t saliency, int64_t* counts_host, float* exp_host, float* scores_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPILOGOS_B200_H */

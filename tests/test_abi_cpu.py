@@ -1,0 +1,49 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU and exports every symbol the header declares;
+compute entry points fail loudly (no CPU fallback) when there is no device."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from epilogos_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def header_functions():
+    text = (ROOT / "include" / "epilogos_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(epi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = header_functions()
+    assert "epi_bin_counts" in names and "epi_single_host" in names
+    for name in names:
+        assert hasattr(lib, name), "symbol %s declared in include/epilogos_b200.h is not exported" % name
+
+
+def test_ctypes_prototypes_cover_header():
+    from epilogos_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == header_functions()
+
+
+def test_abi_version(lib):
+    assert lib.epi_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from epilogos_b200 import _lib
+    with pytest.raises(_lib.EpilogosB200Error):
+        _lib.call("epi_bin_counts", ctypes.c_void_p(16), 1, 1, 16, 18, ctypes.c_void_p(16), ctypes.c_void_p(0))
+    msg = lib.epi_last_error().decode()
+    assert "no CPU fallback" in msg or "CUDA" in msg

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Bit-exact for counts, integer tables and the float32 expected payload.  Scores: float64 output within
+1e-9 relative + 1e-12 absolute of the numpy float64 restatement (BASELINE.json north_star tolerance);
+float32 output equal to the reference's float32 except for <= 1-ulp rounding-boundary cases.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import epilogos_oracle as orc            # noqa: E402  (checker only)
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from epilogos_b200 import build, engine
+    build.build()
+    engine.device_info()
+    return engine
+
+
+def dev_states(eng, x):
+    return eng.pack_states(x).cuda()
+
+
+def gpu_counts(eng, x, k):
+    return eng.counts_to_numpy(eng.bin_counts(dev_states(eng, x), x.shape[1], k))
+
+
+def assert_f32_close(got32, ref32, max_ulp_frac=2e-3):
+    """float32 results equal except rounding-boundary cases (at most 1 ulp apart, and rare)."""
+    got32 = np.asarray(got32); ref32 = np.asarray(ref32)
+    neq = got32 != ref32
+    if neq.any():
+        a = got32[neq].astype(np.float64); b = ref32[neq].astype(np.float64)
+        ulp = np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32)).astype(np.float64)
+        assert np.all(np.abs(a - b) <= ulp * 1.0000001), "float32 scores differ by more than 1 ulp"
+        assert neq.mean() <= max_ulp_frac, "too many 1-ulp differences: %g" % neq.mean()
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("bins,cols,k", [
+    (1, 1, 2), (5, 15, 3), (31, 16, 15), (33, 17, 16), (127, 48, 17), (129, 49, 18), (300, 143, 18),
+    (257, 144, 18), (1000, 145, 25), (700, 833, 18), (515, 833, 15), (260, 127, 15), (130, 1000, 18),
+    (140, 2100, 18), (150, 1700, 16), (135, 1100, 32), (4096, 10, 18), (10000, 833, 18),
+])
+def test_bin_counts_match_oracle(eng, bins, cols, k):
+    rng = np.random.default_rng(bins * 7919 + cols * 31 + k)
+    x = rng.integers(0, k, size=(bins, cols)).astype(np.int8)
+    x[rng.random(bins) < 0.3] = k - 1                         # whole rows of the last state
+    got = gpu_counts(eng, x, k)
+    ref = orc.bin_counts(x, k)
+    assert got.dtype == np.uint16 and got.shape == (bins, k)
+    assert np.array_equal(got.astype(np.int64), ref)
+
+
+def test_bin_counts_any_pitch_and_alignment(eng):
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 18, size=(777, 833)).astype(np.int8)
+    dense = torch.from_numpy(x).cuda()                        # pitch == cols == 833: repacked on the device
+    got = eng.counts_to_numpy(eng.bin_counts(dense, 833, 18))
+    assert np.array_equal(got.astype(np.int64), orc.bin_counts(x, 18))
+    wide = torch.full((777, 1024), 7, dtype=torch.int8, device="cuda")   # garbage in the pad columns
+    wide[:, :833] = dense
+    got = eng.counts_to_numpy(eng.bin_counts(wide, 833, 18))
+    assert np.array_equal(got.astype(np.int64), orc.bin_counts(x, 18))
+
+
+def test_bin_counts_empty(eng):
+    out = eng.bin_counts(torch.zeros((0, 848), dtype=torch.int8, device="cuda"), 833, 18)
+    assert out.shape == (0, 18)
+
+
+def test_bad_arguments_raise(eng):
+    from epilogos_b200._lib import EpilogosB200Error
+    x = torch.zeros((4, 16), dtype=torch.int8, device="cuda")
+    with pytest.raises(EpilogosB200Error):
+        eng.bin_counts(x, 16, 33)
+    with pytest.raises(EpilogosB200Error):
+        eng.bin_counts(x, 17, 18)
+
+
+# ------------------------------------------------------------------------------------ K2 / K4 / K5
+SINGLE = ["real10_chr1_k18", "real10_chr1_k18_nproc3", "synth_c833_k18", "synth_uniform_c833_k18", "synth_c127_k15"]
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_tables_and_scores_match_reference_goldens(eng, golden, name):
+    g = golden(name)
+    x, k = g["x"], int(g["num_states"])
+    c = x.shape[1]
+    cnt = eng.bin_counts(dev_states(eng, x), c, k)
+    n1, n2 = eng.expected_tables(cnt, c)
+    assert np.array_equal(n1.cpu().numpy(), g["s1_counts"])
+    assert np.array_equal(n2.cpu().numpy(), g["s2_counts"])
+    e1, e2 = eng.normalize(n1), eng.normalize(n2)
+    assert e1.cpu().numpy().tobytes() == g["s1_exp"].tobytes()
+    assert e2.cpu().numpy().tobytes() == g["s2_exp"].tobytes()
+    ref1_64 = orc.s1_scores(x, k, g["s1_exp"], dtype=np.float64)
+    ref2_64 = orc.s2_scores(x, k, g["s2_exp"], dtype=np.float64)
+    for mode in (eng.EPI_SCORE_TABLE, eng.EPI_SCORE_DIRECT):
+        s1_32, s1_64 = eng.scores_s1(cnt, c, e1, want64=True, mode=mode)
+        s2_32, s2_64 = eng.scores_s2(cnt, c, e2, want64=True, mode=mode)
+        np.testing.assert_allclose(s1_64.cpu().numpy(), ref1_64, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(s2_64.cpu().numpy(), ref2_64, rtol=RTOL, atol=ATOL)
+        assert_f32_close(s1_32.cpu().numpy(), g["s1_scores"])
+        assert_f32_close(s2_32.cpu().numpy(), g["s2_scores"])
+
+
+@pytest.mark.parametrize("k,cols", [(25, 60), (32, 200), (16, 90), (17, 300), (3, 2)])
+def test_other_state_models(eng, k, cols):
+    rng = np.random.default_rng(k * 100 + cols)
+    x = rng.integers(0, k, size=(900, cols)).astype(np.int8)
+    cnt = eng.bin_counts(dev_states(eng, x), cols, k)
+    n1, n2 = eng.expected_tables(cnt, cols)
+    assert np.array_equal(n1.cpu().numpy(), orc.s1_expected_counts(x, k))
+    assert np.array_equal(n2.cpu().numpy(), orc.s2_expected_counts(x, k))
+    e1, e2 = eng.normalize(n1), eng.normalize(n2)
+    assert e1.cpu().numpy().tobytes() == orc.normalize_expected(n1.cpu().numpy()).tobytes()
+    assert e2.cpu().numpy().tobytes() == orc.normalize_expected(n2.cpu().numpy()).tobytes()
+    for mode in (eng.EPI_SCORE_TABLE, eng.EPI_SCORE_DIRECT):
+        _, s1_64 = eng.scores_s1(cnt, cols, e1, want64=True, mode=mode)
+        _, s2_64 = eng.scores_s2(cnt, cols, e2, want64=True, mode=mode)
+        np.testing.assert_allclose(s1_64.cpu().numpy(), orc.s1_scores(x, k, e1.cpu().numpy(), np.float64),
+                                   rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(s2_64.cpu().numpy(), orc.s2_scores(x, k, e2.cpu().numpy(), np.float64),
+                                   rtol=RTOL, atol=ATOL)
+
+
+def test_foreign_expected_table_with_zeros_is_masked(eng):
+    """klScoreND masks terms whose expected frequency is 0 (scores.py:550); a table computed from other
+    data can have zeros where this data has observations."""
+    rng = np.random.default_rng(77)
+    k, cols = 18, 50
+    x = rng.integers(0, k, size=(400, cols)).astype(np.int8)
+    e1 = orc.normalize_expected(orc.s1_expected_counts(x, k)).copy()
+    e2 = orc.normalize_expected(orc.s2_expected_counts(x, k)).copy()
+    e1[[2, 9]] = 0
+    e2[3, :] = 0; e2[:, 11] = 0; e2[5, 5] = 0
+    cnt = eng.bin_counts(dev_states(eng, x), cols, k)
+    _, s1 = eng.scores_s1(cnt, cols, torch.from_numpy(e1).cuda(), want64=True)
+    _, s2 = eng.scores_s2(cnt, cols, torch.from_numpy(e2).cuda(), want64=True)
+    np.testing.assert_allclose(s1.cpu().numpy(), orc.s1_scores(x, k, e1, np.float64), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(s2.cpu().numpy(), orc.s2_scores(x, k, e2, np.float64), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("name,sal", [("real10_chr1_k18", 1), ("real10_chr1_k18", 2), ("synth_c833_k18", 2),
+                                      ("synth_c127_k15", 1), ("synth_c127_k15", 2)])
+def test_single_host_entry_point(eng, golden, name, sal):
+    g = golden(name)
+    x, k = g["x"], int(g["num_states"])
+    counts, exp, scores = eng.single_host(np.ascontiguousarray(x), x.shape[1], k, sal)   # dense pitch, pageable
+    assert np.array_equal(counts, g["s%d_counts" % sal])
+    assert exp.tobytes() == g["s%d_exp" % sal].tobytes()
+    assert_f32_close(scores, g["s%d_scores" % sal])
+    counts2, exp2, scores2 = eng.single_host(eng.pack_states(x), x.shape[1], k, sal)      # pinned, padded pitch
+    assert np.array_equal(counts2, counts) and exp2.tobytes() == exp.tobytes()
+    assert np.array_equal(scores2, scores)
+
+
+# -------------------------------------------------------------------------------- full-size properties
+def test_whole_genome_shape_properties(eng):
+    """BASELINE config 2 width (833 biosamples, 18 states) at 2 M bins: size-independent invariants."""
+    from epilogos_b200 import synth
+    bins, cols, k = 2_000_000, 833, 18
+    x = synth.synth_states_device(bins, cols, k, seed=21)
+    cnt = eng.bin_counts(x, cols, k)
+    c64 = cnt.to(torch.int32) & 0xFFFF
+    assert bool((c64.sum(dim=1) == cols).all())                       # every label counted exactly once
+    n1, n2 = eng.expected_tables(cnt, cols)
+    hist = torch.zeros(k, dtype=torch.int64, device="cuda")
+    for lo in range(0, bins, 1 << 18):
+        hist += torch.bincount(x[lo:lo + (1 << 18), :cols].reshape(-1).to(torch.int64), minlength=k)
+    assert torch.equal(n1, hist)                                      # independent histogram of the labels
+    assert int(n1.sum()) == bins * cols
+    assert int(n2.sum()) == bins * cols * (cols - 1)                  # closed form, SURVEY 8a
+    assert torch.equal(n2, n2.T) and bool((n2 >= 0).all())
+    assert torch.equal(n2.sum(dim=1), n1 * (cols - 1))
+    e2 = eng.normalize(n2)
+    s2 = eng.scores_s2(cnt, cols, e2)
+    assert bool(torch.isfinite(s2).all())
+    # spot-check 2000 bins against the oracle
+    idx = torch.randperm(bins, device="cuda")[:2000]
+    xs = x[idx, :cols].cpu().numpy()
+    ref = orc.s2_scores(xs, k, e2.cpu().numpy(), dtype=np.float64)
+    _, s2_64 = eng.scores_s2(cnt[idx].contiguous(), cols, e2, want64=True)
+    np.testing.assert_allclose(s2_64.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
