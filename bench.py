@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- bins/sec for expected + scores on B200 (BASELINE.json metric), plus the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--saliency 2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic matrix that is already resident in HBM:
+K1 counts -> K2 expected table -> (allreduce over ranks) -> K4 normalise -> K5 scores.
+Workload at every N: BASELINE.json configs[1], S2 on 15.5 M bins x 833 biosamples x 18 states PER GPU
+(weak scaling; the bins shard with no data-path collective, only the 18x18 table is all-reduced).
+The matrix (13 GB) is far larger than L2 (126 MB), so no L2 flush is needed between steps.
+
+`e2e` is the same metric through epi_single_host (the reference-facing C-ABI call) with the matrix in
+pinned HOST memory: H2D of the matrix and D2H of tables + scores are inside the timed region.
+
+`--impl reference` times the CPU restatement of the reference's row-loop algorithm (oracle/, kind "port":
+the reference is pure Python and cannot travel to the GPU box) with all host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GENOME_BINS = 15_500_000
+CONFIGS = {
+    # name: (bins per GPU, biosamples, states, description)
+    "s2_genome_833": (GENOME_BINS, 833, 18, "S2 whole-genome 15.5M bins x 833 biosamples, 18-state (BASELINE configs[1])"),
+    "s2_genome_127": (GENOME_BINS, 127, 15, "S2 whole-genome 15.5M bins x 127 biosamples, 15-state (BASELINE configs[4])"),
+    "s1_chr1_833": (1_246_253, 833, 18, "S1 chr1 1,246,253 bins x 833 biosamples, 18-state (shape of BASELINE configs[0])"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="s2_genome_833", choices=sorted(CONFIGS))
+    ap.add_argument("--bins", type=int, default=0, help="override bins per GPU (debug)")
+    ap.add_argument("--kind", default="realistic", choices=["realistic", "uniform"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's row-loop port of expected+scores, all host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    from oracle import epilogos_oracle as orc
+    bins, cols, k, saliency, seed, phase, exp = args
+    x = orc.synth_states(bins, cols, k, seed)
+    if phase == "expected":
+        if saliency == 1:
+            return orc.s1_expected_counts_rowloop(x, k)
+        return orc.s2_expected_counts_rowloop(x, k)
+    if saliency == 1:
+        return orc.s1_scores_rowloop(x, k, exp).sum()
+    return orc.s2_scores_rowloop(x, k, exp).sum()
+
+
+def cpu_port_pass(pool, cores, bins_per_core, cols, k, saliency, seed0):
+    """expected.main -> expectedCombination.main -> scores.main on cores*bins_per_core bins, one row range
+    per worker process (the reference's multiprocessing.Pool fan-out, expected.py:71-79, scores.py:147-154).
+    Returns seconds spent in the two compute phases (synthetic chunk generation included in the workers is
+    measured separately and subtracted)."""
+    from oracle import epilogos_oracle as orc
+    jobs = [(bins_per_core, cols, k, saliency, seed0 + i, "expected", None) for i in range(cores)]
+    t0 = time.perf_counter()
+    parts = pool.map(_cpu_worker, jobs)
+    exp = orc.normalize_expected(sum(parts))
+    jobs = [(bins_per_core, cols, k, saliency, seed0 + i, "scores", exp) for i in range(cores)]
+    pool.map(_cpu_worker, jobs)
+    return time.perf_counter() - t0
+
+
+def _gen_worker(args):
+    from oracle import epilogos_oracle as orc
+    bins, cols, k, seed = args
+    return int(orc.synth_states(bins, cols, k, seed).sum())
+
+
+def cpu_baseline(cols, k, saliency, budget_s=12.0, steps=1, warmup=0):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        # calibrate on a small pass, then size the sample for ~budget_s
+        probe = 64
+        t = cpu_port_pass(pool, cores, probe, cols, k, saliency, 1000)
+        tg0 = time.perf_counter()
+        pool.map(_gen_worker, [(probe, cols, k, 1000 + i) for i in range(cores)])
+        tgen = 2 * (time.perf_counter() - tg0)
+        rate = probe / max(t - tgen, 1e-3)
+        per_core = int(max(64, min(20000, rate * budget_s)))
+        times = []
+        for it in range(warmup + steps):
+            tt = cpu_port_pass(pool, cores, per_core, cols, k, saliency, 2000 + 100 * it)
+            tg0 = time.perf_counter()
+            pool.map(_gen_worker, [(per_core, cols, k, 2000 + 100 * it + i) for i in range(cores)])
+            tgen = 2 * (time.perf_counter() - tg0)
+            if it >= warmup:
+                times.append(max(tt - tgen, 1e-6))
+    total = per_core * cores
+    sec = sum(times) / len(times)
+    return dict(value=total / sec, unit="bins/s", cores=cores, kind="port",
+                sample="%d bins x %d biosamples x %d states (S%d expected+scores, %d worker processes x %d bins, "
+                       "row-loop port of expected.py/scores.py, I/O excluded)" % (total, cols, k, saliency, cores,
+                                                                                  per_core)), sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bins, cols, k, desc = CONFIGS[args.config]
+    saliency = 1 if args.config.startswith("s1") else 2
+    base, sec = cpu_baseline(cols, k, saliency, budget_s=6.0, steps=max(1, args.steps), warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "bins/sec for expected+scores (S%d)" % saliency, "value": base["value"],
+        "unit": "bins/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": desc, "biosamples": cols, "states": k, "saliency": saliency,
+                   "note": "each step is a bounded sample of the workload on the host CPU"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling through NVML while the timed region runs
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv is not None:
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.nv is not None and self.thread.is_alive():
+            self.thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "power_w_max": max(self.power) if self.power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from epilogos_b200 import engine, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bins, cols, k, desc = CONFIGS[args.config]
+    if args.bins:
+        bins = args.bins
+    saliency = 1 if args.config.startswith("s1") else 2
+    engine.device_info()
+
+    x = synth.synth_states_device(bins, cols, k, seed=1234 + rank, kind=args.kind)
+    cnt = torch.empty((bins, k), dtype=torch.int16, device="cuda")
+    scores = torch.empty((bins, k), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    k1_ev = []
+
+    def step(timed):
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        engine.bin_counts(x, cols, k, out=cnt)                               # K1
+        if timed:
+            e1.record(stream)
+            k1_ev.append((e0, e1))
+        n1, n2 = engine.expected_tables(cnt, cols, want_s1=saliency == 1, want_s2=saliency == 2)   # K2
+        n = n1 if saliency == 1 else n2
+        if world > 1:
+            dist.all_reduce(n)                                               # the path's only exchange
+        e = engine.normalize(n)                                              # K4 (2 kernels)
+        if saliency == 1:
+            engine.scores_s1(cnt, cols, e, out32=scores)                     # K5
+        else:
+            engine.scores_s2(cnt, cols, e, out32=scores)
+        return e
+
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
+    k1_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k1_ev) / len(k1_ev)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(k1_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(elapsed_ms.item()) / args.steps
+    value = bins * world / (ms_per_step * 1e-3)
+    k1_ms = float(k1_ms.item())
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        host = None
+        e2e_bins = bins
+        while host is None and e2e_bins >= 1024:
+            try:
+                host = torch.empty((e2e_bins, x.shape[1]), dtype=torch.int8, pin_memory=True)
+            except RuntimeError:
+                e2e_bins //= 2
+        host.copy_(x[:e2e_bins])
+        torch.cuda.synchronize()
+        engine.single_host(host, cols, k, saliency)                          # warm-up (allocations)
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(args.e2e_steps):
+            tic = time.perf_counter()
+            engine.single_host(host, cols, k, saliency)
+            times.append(time.perf_counter() - tic)
+        t = torch.tensor([sum(times) / len(times)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ntab = k if saliency == 1 else k * k
+        e2e = {"value": e2e_bins * world / float(t.item()), "unit": "bins/s",
+               "h2d_bytes_per_step": e2e_bins * int(x.shape[1]), "d2h_bytes_per_step": e2e_bins * k * 4 + ntab * 12,
+               "bins_per_gpu": e2e_bins, "steps": args.e2e_steps,
+               "api": "epi_single_host (C ABI, pinned host matrix in, tables + float32 scores out)"}
+        del host
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = bins * cols / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "roofline_traffic.json"
+        if tf.exists():
+            try:
+                per_bin = json.loads(tf.read_text()).get(args.config, {}).get("k1_dram_bytes_per_bin")
+                traffic = per_bin * bins if per_bin else None
+            except Exception:
+                traffic = None
+        step_alg = bins * (cols + 4 * k)
+        line = {
+            "metric": "bins/sec for expected+scores (S%d)" % saliency, "value": value, "unit": "bins/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "bins_per_gpu": bins, "biosamples": cols, "states": k, "saliency": saliency,
+                       "distribution": args.kind, "parallelism": "bins sharded x%d, int64 table allreduce" % world,
+                       "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (bins * x.shape[1] / 1e9)},
+            "roofline": {"bound": "hbm", "kernel": "k1_counts_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bins * cols, "ms_per_launch": k1_ms},
+            "step_roofline": {"algorithmic_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
+                              "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+            "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _ = cpu_baseline(cols, k, saliency)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

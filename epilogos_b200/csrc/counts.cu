@@ -391,9 +391,9 @@ extern "C" int epi_bin_counts(const int8_t* x_dev, int64_t bins, int32_t cols, i
     EPI_REQUIRE(pitch >= cols, "pitch=%lld smaller than cols=%d", (long long)pitch, cols);
     EPI_REQUIRE(num_states >= 1 && num_states <= EPI_MAX_STATES, "num_states=%d out of range [1, %d]", num_states,
                 EPI_MAX_STATES);
+    if (bins == 0) return 0;
     EPI_REQUIRE(x_dev != nullptr && cnt_dev != nullptr, "null pointer argument");
     EPI_REQUIRE((reinterpret_cast<uintptr_t>(cnt_dev) & 15) == 0, "cnt_dev must be 16-byte aligned");
-    if (bins == 0) return 0;
     if ((pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0)
         return bin_counts_aligned(x_dev, bins, cols, pitch, num_states, cnt_dev, stream);
     // arbitrary pitch / alignment: repack on the device into a 16-byte pitched scratch matrix

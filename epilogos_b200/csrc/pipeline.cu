@@ -97,8 +97,12 @@ extern "C" int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols,
         const int64_t lo = c * chunk;
         const int64_t nb = (bins - lo) < chunk ? (bins - lo) : chunk;
         if (c >= 2) EPI_CUDA(cudaStreamWaitEvent(hp.copy, hp.counted[b], 0));
-        EPI_CUDA(cudaMemcpy2DAsync(hp.xbuf[b], (size_t)dpitch, x_host + lo * pitch, (size_t)pitch, (size_t)cols,
-                                   (size_t)nb, cudaMemcpyHostToDevice, hp.copy));
+        if (pitch == dpitch)   // already in the device layout: one contiguous DMA (pad bytes travel, never read)
+            EPI_CUDA(cudaMemcpyAsync(hp.xbuf[b], x_host + lo * pitch, (size_t)(nb * pitch), cudaMemcpyHostToDevice,
+                                     hp.copy));
+        else
+            EPI_CUDA(cudaMemcpy2DAsync(hp.xbuf[b], (size_t)dpitch, x_host + lo * pitch, (size_t)pitch, (size_t)cols,
+                                       (size_t)nb, cudaMemcpyHostToDevice, hp.copy));
         EPI_CUDA(cudaEventRecord(hp.copied[b], hp.copy));
         EPI_CUDA(cudaStreamWaitEvent(hp.compute, hp.copied[b], 0));
         if (int rc = epi_bin_counts(hp.xbuf[b], nb, cols, dpitch, K, hp.cnt + lo * K, hp.compute)) return rc;

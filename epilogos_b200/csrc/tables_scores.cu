@@ -152,6 +152,11 @@ __global__ void k4_divide_kernel(const long long* __restrict__ counts, long long
 // ================================================================================================
 constexpr int K5_THREADS = 256;
 
+template <class T>
+__device__ __forceinline__ T* align16(const void* p) {
+    return reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15));
+}
+
 __device__ __forceinline__ double kl_direct(double obs, double e) {
     // klScoreND (scores.py:550): 0 where E == 0 (masked divide) or obs/E <= 0 (masked log2)
     if (e == 0.0 || obs == 0.0) return 0.0;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __res
     double* le_s = e_s + K;                                                       // K   log2(width * E)
     double* lc = le_s + K;                                                        // width + 1 (USE_LC)
     double* ot = lc + (USE_LC ? width + 1 : 0);                                   // width + 1 (USE_LC)
-    uint16_t* tile = reinterpret_cast<uint16_t*>(ot + (USE_LC ? width + 1 : 0));  // K5_THREADS * K
+    uint16_t* tile = align16<uint16_t>(ot + (USE_LC ? width + 1 : 0));            // K5_THREADS * K
 
     const int tid = threadIdx.x;
     const double dw = (double)width;
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
     double* m_s = stage + K5_THREADS * K;                                         // KT * KT  log2(P*E), [s][t]
     double* e_s = m_s + KT * KT;                                                  // K * K    E as double
     double* lc = e_s + K * K;                                                     // width + 1
-    uint16_t* tile = reinterpret_cast<uint16_t*>(lc + (USE_LC ? width + 1 : 0));  // K5_THREADS * K
+    uint16_t* tile = align16<uint16_t>(lc + (USE_LC ? width + 1 : 0));            // K5_THREADS * K
 
     const int tid = threadIdx.x;
     __shared__ int any_zero;
@@ -398,7 +403,7 @@ static int check_common(const void* cnt, int64_t bins, int K) {
     if (check_device()) return 3;
     EPI_REQUIRE(bins >= 0 && bins < (1ll << 31), "bins=%lld out of range", (long long)bins);
     EPI_REQUIRE(K >= 1 && K <= EPI_MAX_STATES, "num_states=%d out of range [1, %d]", K, EPI_MAX_STATES);
-    EPI_REQUIRE(cnt != nullptr, "null count pointer");
+    EPI_REQUIRE(cnt != nullptr || bins == 0, "null count pointer");
     EPI_REQUIRE((reinterpret_cast<uintptr_t>(cnt) & 15) == 0, "cnt_dev must be 16-byte aligned");
     return 0;
 }
