@@ -1,0 +1,43 @@
+"""The compute provider used by the stage drivers.
+
+CudaBackend is the product: every method is a call into libepilogos_b200.so (via engine) on the current
+CUDA device, and it raises if the library or a B200 is missing -- there is no CPU fallback.  The stage
+drivers take the backend as a parameter only so that the CPU-only unit tests can exercise the
+sharding / all-reduce / gather / file-naming logic with a stand-in defined under tests/.
+"""
+import torch
+
+from . import engine
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("epilogos_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        engine.device_info()
+
+    # -- per-bin counts of a shard (numpy int8 [rows, C], 0-based) -> device tensor [rows, K] (uint16 in int16)
+    def counts(self, states0, num_states):
+        x = engine.pack_states(states0).to(self.device, non_blocking=True)
+        return engine.bin_counts(x, states0.shape[1], num_states)
+
+    # -- integer expected table of the shard: int64 [K] (S1) or [K, K] (S2), on the device
+    def expected_table(self, cnt, width, saliency):
+        n1, n2 = engine.expected_tables(cnt, width, want_s1=saliency == 1, want_s2=saliency == 2)
+        return n1 if saliency == 1 else n2
+
+    def normalize(self, counts):
+        return engine.normalize(counts.to(self.device))
+
+    def to_device(self, array):
+        return torch.as_tensor(array).to(self.device)
+
+    # -- float32 scores [rows, K] of the shard
+    def scores(self, cnt, width, saliency, exp, perms=None):
+        exp = exp.to(self.device).contiguous()
+        if saliency == 1:
+            return engine.scores_s1(cnt, width, exp)
+        return engine.scores_s2(cnt, width, exp, perms=perms)

@@ -22,6 +22,8 @@
 //    aliased states are separated exactly from sum(v) and sum(v^2), which cost one IDP4A each per
 //    4 bytes.  Models with more than 18 states use one-bit one-hot words (2 LOP3 per byte).
 //  * counts leave through shared memory as coalesced 16-byte stores of uint16 [bins][K].
+#include <stdlib.h>
+
 #include <utility>
 
 #include "common.cuh"
@@ -39,16 +41,27 @@ struct PlaneCount {
     static constexpr int CAP = (1 << N) - 1;                    // words that may be added before a flush
 };
 
-// Per-chunk register image of one row: shift-amount words (2*v per byte for 2-bit fields, v for 1-bit).
+// Per-chunk register image of one row (the raw label words).  Pipe balance matters here: the kernel is bound
+// by the integer ALU pipe (SHF/LOP3/IADD3, 64 lanes/clk/SM), while the FMA pipe (IMAD/IDP, 128 lanes/clk/SM)
+// is nearly idle.  So byte extraction and the 3-way sums are expressed as IDP.4A / IMAD, which leaves
+// one SHF per byte (the one-hot) and the carry-save LOP3s on the ALU pipe.
 template <int BV, int MODE>
 struct ChunkSrc {
     uint32_t w[4 * BV];
+    uint32_t one;      // the value 1, opaque to the compiler so that x*one+y stays an IMAD
 
+    // shift amount for byte `lane` of word `word`: 2*v (two-bit fields) or v (one-bit), possibly with
+    // garbage above bit 4 for lane 0 -- the wrap-mode funnel shift reads only the low 5 bits.
     template <int J>
     __device__ __forceinline__ uint32_t onehot() const {
         constexpr int word = J >> 2, lane = J & 3;
-        // 1 << (sh mod 32): the funnel shifter in wrap mode reads only the low 5 bits of the amount
-        const uint32_t sh = (lane == 0) ? w[word] : (w[word] >> (8 * lane));
+        constexpr uint32_t mul = (MODE == MODE_B1) ? 1u : 2u;
+        uint32_t sh;
+        if constexpr (lane == 0) {
+            sh = (MODE == MODE_B1) ? w[word] : w[word] + w[word];
+        } else {
+            sh = __dp4a(w[word], mul << (8 * lane), 0u);              // IDP.4A: byte `lane` times mul (FMA pipe)
+        }
         uint32_t r;
         asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(1u), "r"(sh));
         return r;
@@ -58,7 +71,11 @@ struct ChunkSrc {
         if constexpr (MODE == MODE_B1) {
             return onehot<I>();
         } else {
-            return onehot<3 * I>() + onehot<3 * I + 1>() + onehot<3 * I + 2>();
+            // two IMAD (x*1+y) instead of one IADD3: keeps the sum off the ALU pipe
+            uint32_t t;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(onehot<3 * I>()), "r"(one), "r"(onehot<3 * I + 1>()));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(onehot<3 * I + 2>()), "r"(one), "r"(t));
+            return t;
         }
     }
 };
@@ -121,8 +138,9 @@ __device__ __forceinline__ void fold_groups(const ChunkSrc<BV, MODE>& src, uint3
 
 template <int BV, int MODE, int NP>
 __device__ __forceinline__ void process_chunk(const uint4* __restrict__ row, uint32_t (&p)[NP], uint32_t& sum1,
-                                              uint32_t& sum2) {
+                                              uint32_t& sum2, uint32_t one) {
     ChunkSrc<BV, MODE> src;
+    src.one = one;
 #pragma unroll
     for (int v = 0; v < BV; ++v) {
         const uint4 q = row[v];
@@ -133,7 +151,7 @@ __device__ __forceinline__ void process_chunk(const uint4* __restrict__ row, uin
                 sum1 = __dp4a(qq[i], 0x01010101u, sum1);
                 sum2 = __dp4a(qq[i], qq[i], sum2);
             }
-            src.w[4 * v + i] = (MODE == MODE_B1) ? qq[i] : qq[i] + qq[i];
+            src.w[4 * v + i] = qq[i];
         }
     }
     constexpr int NG = (MODE == MODE_B1) ? BV : BV / 3;      // groups of 16 words
@@ -147,11 +165,9 @@ __device__ __forceinline__ void flush_planes(uint32_t (&p)[NP], uint32_t (&acc)[
     for (int k = 0; k < NP; ++k) {
 #pragma unroll
         for (int f = 0; f < NACC; ++f) {
-            if constexpr (MODE == MODE_B1) {
-                acc[f] += ((p[k] >> f) & 0x00010001u) << k;            // lo: state f, hi: state f+16
-            } else {
-                acc[f] += ((p[k] >> (2 * f)) & 0x00030003u) << k;      // lo: field f, hi: field f+8
-            }
+            // lo half: state/field f, hi half: state f+16 / field f+8.  acc += t * 2^k as one IMAD.
+            const uint32_t t = (MODE == MODE_B1) ? ((p[k] >> f) & 0x00010001u) : ((p[k] >> (2 * f)) & 0x00030003u);
+            asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[f]) : "r"(t), "r"(1u << k));
         }
         p[k] = 0;
     }
@@ -160,7 +176,7 @@ __device__ __forceinline__ void flush_planes(uint32_t (&p)[NP], uint32_t (&acc)[
 template <int BV, int MODE>
 __global__ void __launch_bounds__(K1_THREADS, (BV <= 9 ? 3 : 2))
 k1_counts_kernel(const __grid_constant__ CUtensorMap tmap, long long bins, int nchunks, int flush_chunks, int npad,
-                 int num_states, int stages, uint16_t* __restrict__ cnt) {
+                 int num_states, int stages, uint32_t one, uint16_t* __restrict__ cnt) {
     constexpr int NP = PlaneCount<MODE>::N;
     constexpr int NACC = (MODE == MODE_B1) ? 16 : 8;
     constexpr int STAGE_BYTES = BV * 16 * K1_ROWS;
@@ -224,7 +240,7 @@ k1_counts_kernel(const __grid_constant__ CUtensorMap tmap, long long bins, int n
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&full[s], ph);
             const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)s * STAGE_BYTES + tid * (BV * 16));
-            process_chunk<BV, MODE, NP>(row, p, sum1, sum2);
+            process_chunk<BV, MODE, NP>(row, p, sum1, sum2, one);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == stages) {
@@ -330,8 +346,10 @@ template <int BV, int MODE>
 static int launch_k1(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, int num_states, uint16_t* cnt,
                           cudaStream_t stream) {
     constexpr int stage_bytes = BV * 16 * K1_ROWS;
-    const int stages = (BV <= 3) ? 8 : (BV <= 9 ? 4 : 3);
-    const int ctas_per_sm = (BV <= 9) ? 3 : 2;
+    int stages = (BV <= 3) ? 8 : 3;           // measured on B200 at 833 biosamples: 3 stages x 2 CTAs/SM is best
+    int ctas_per_sm = (BV <= 3) ? 3 : 2;
+    if (const char* e = getenv("EPI_K1_STAGES")) stages = atoi(e) > 0 ? atoi(e) : stages;      // tuning knobs
+    if (const char* e = getenv("EPI_K1_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;
     const size_t smem = (size_t)stages * stage_bytes + ((K1_ROWS * num_states * 2 + 15) & ~15) + 2 * stages * 8;
     auto kern = k1_counts_kernel<BV, MODE>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -342,7 +360,7 @@ static int launch_k1(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, in
     int64_t grid = (int64_t)sm_count() * ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, K1_THREADS, smem, stream>>>(tmap, (long long)bins, pl.nchunks, flush_chunks, pl.npad,
-                                                        num_states, stages, cnt);
+                                                        num_states, stages, 1u, cnt);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,357 @@
+// K5 -- S1 / S2 Kullback-Leibler scores from the per-bin uint16 counts.
+//
+//   S1: score[s] = o log2(o / E1[s]),            o    = c_s / width            (scores.py:339-344, 317, 550)
+//   S2: score[t] = sum_s o_st log2(o_st / E2[s][t]),
+//                  o_st = (c_s c_t - [s==t] c_s) / P, added in order s = 0..K-1 (scores.py:443-451, 412, 550)
+//   terms with o == 0 or E == 0 are 0 (numpy.ma masking in klScoreND).
+//
+// Traffic per bin: 2K bytes of counts in, 4K bytes of float32 scores out (36 + 72 B at K = 18); the work is
+// float64 arithmetic.  A term-by-term evaluation costs a correctly rounded divide and a log2 per (s,t) pair
+// (171 distinct pairs per bin at K = 18: ~35 ms per 15.5 M bins on the fp64 pipe).  The TABLE path removes
+// the transcendentals from the per-bin work:
+//      log2(o_st / E_st) = L(c_s) + L(c_t) - log2 P - log2 E_st,      L = log2 of an integer count (table)
+//      score[t] = (c_t / P) * { [A + W (L(c_t) - log2 P) - (LE c)_t]
+//                               - c_t (2 L(c_t) - log2 P - LE_tt) + (c_t - 1)(L(c_t) + L(c_t - 1) - log2 P - LE_tt) }
+//      A = sum_s c_s L(c_s),  W = sum_s c_s,  (LE c)_t = sum_s c_s log2 E_st
+// i.e. one 18x18 mat-vec in DFMAs per bin.  LE lives in __constant__ memory so the DFMAs take it as a
+// constant-bank operand (no load instructions); it is rebuilt from the float32 table on every call.
+// The result differs from the term-by-term float64 evaluation by rounding only (tests: 1e-9 relative +
+// 1e-12 absolute).  Whenever E has a zero entry (a foreign expected table) the kernel switches to the
+// DIRECT evaluation, which implements the masked-term semantics literally.
+//
+// I/O is staged per warp (no block-wide barriers in the steady state): 32 bins of counts come in as 16-byte
+// vectors, 32 rows of float32 scores leave as 16-byte vectors.
+#include "common.cuh"
+
+namespace epi {
+
+constexpr int K5_THREADS = 256;
+constexpr int K5_WARPS = K5_THREADS / 32;
+constexpr int LC_MAX_WIDTH = 2047;        // log2(count) / count/width tables live in shared memory up to this width
+constexpr int KT_MAX = EPI_MAX_STATES;
+
+__constant__ double c_log2e[KT_MAX * KT_MAX];     // S2: log2 E[s][t], row stride KT; S1: log2 E[s]
+
+struct PrepFlags {
+    int has_zero;       // some expected frequency is 0 -> masked terms -> DIRECT evaluation
+};
+
+// one CTA: expected table (float32) -> log2 table (float64, row stride kt) + zero flag, in device scratch
+__global__ void k5_prepare_kernel(const float* __restrict__ e, int rows, int cols, int kt, double* __restrict__ out,
+                                  PrepFlags* flags) {
+    __shared__ int zero;
+    if (threadIdx.x == 0) zero = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * kt; i += blockDim.x) {
+        const int s = i / kt, q = i - s * kt;
+        double v = 0.0;
+        if (q < cols) {
+            const double ev = (double)e[s * cols + q];
+            if (ev > 0.0) v = log2(ev);
+            else zero = 1;
+        }
+        out[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) flags->has_zero = zero;
+}
+
+__device__ __forceinline__ double kl_direct(double obs, double e) {
+    // klScoreND (scores.py:550): 0 where E == 0 (masked divide) or obs/E <= 0 (masked log2)
+    if (e == 0.0 || obs == 0.0) return 0.0;
+    return obs * log2(obs / e);
+}
+
+// ---- per-warp staging helpers -------------------------------------------------------------------
+// Per-warp stream of 32-bin count groups: two slabs filled by 1D bulk copies (cp.async.bulk + mbarrier), the
+// group after the current one is always in flight while the warp computes.  The partial group at the end of
+// the array is read with plain loads.
+struct WarpCountStream {
+    const uint16_t* cnt;
+    uint16_t* slab[2];
+    uint64_t* bar;        // two mbarriers
+    long long bins, ngroups, stride;
+    int K, lane, buf;
+    uint32_t phase[2];
+
+    __device__ __forceinline__ void issue(long long g, int b) const {
+        if (lane == 0 && g < ngroups && bins - g * 32 >= 32) {
+            mbar_expect_tx(&bar[b], 64 * K);
+            bulk_load_1d(slab[b], cnt + g * 32 * K, 64 * K, &bar[b]);
+        }
+    }
+    // returns the slab holding group g (its first nvalid rows); prefetches group g + stride
+    __device__ __forceinline__ const uint16_t* acquire(long long g, int nvalid) {
+        const int b = buf;
+        buf ^= 1;
+        issue(g + stride, b ^ 1);
+        if (nvalid == 32) {
+            mbar_wait(&bar[b], phase[b]);
+            phase[b] ^= 1;
+        } else {
+            const uint16_t* src = cnt + g * 32 * K;
+            for (int i = lane; i < nvalid * K; i += 32) slab[b][i] = src[i];
+            __syncwarp();
+        }
+        return slab[b];
+    }
+};
+
+// the warp's 32 rows of float scores -> global (16-byte stores when the group is full)
+__device__ __forceinline__ void warp_store_scores(const float* slab, float* __restrict__ dst, int nvalid, int K,
+                                                  int lane) {
+    __syncwarp();
+    if (nvalid == 32) {
+        const float4* s4 = reinterpret_cast<const float4*>(slab);  // 32*K*4 bytes = 8K vectors
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = lane; i < 8 * K; i += 32) d4[i] = s4[i];
+    } else {
+        for (int i = lane; i < nvalid * K; i += 32) dst[i] = slab[i];
+    }
+    __syncwarp();
+}
+
+// ---- S1 -----------------------------------------------------------------------------------------
+template <bool USE_LC>
+__global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
+                                                           int width, const float* __restrict__ exp1,
+                                                           const PrepFlags* __restrict__ flags, int force_direct,
+                                                           float* __restrict__ out32, double* __restrict__ out64) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint16_t* cslab = reinterpret_cast<uint16_t*>(smem_raw);                          // K5_WARPS * 2 * 32 * K u16
+    float* fslab = reinterpret_cast<float*>(smem_raw + K5_WARPS * 32 * K * 4);        // K5_WARPS * 32 * K f32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K5_WARPS * 32 * K * 8);   // K5_WARPS * 2
+    double* lc = reinterpret_cast<double*>(bars + K5_WARPS * 2);                      // width + 1
+    double* ot = lc + (USE_LC ? width + 1 : 0);                                       // width + 1
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double dw = (double)width;
+    const double lw = log2(dw);
+    if (tid == 0) {
+        for (int i = 0; i < K5_WARPS * 2; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    if (USE_LC) {
+        for (int i = tid; i <= width; i += K5_THREADS) {
+            lc[i] = i > 0 ? log2((double)i) : 0.0;
+            ot[i] = (double)i / dw;
+        }
+    }
+    __syncthreads();
+    const bool direct = force_direct || flags->has_zero;
+    float* myf = fslab + warp * 32 * K;
+
+    const long long ngroups = (bins + 31) / 32;
+    WarpCountStream in{cnt, {cslab + warp * 64 * K, cslab + warp * 64 * K + 32 * K}, bars + warp * 2, bins, ngroups,
+                       (long long)gridDim.x * K5_WARPS, K, lane, 0, {0u, 0u}};
+    in.issue((long long)blockIdx.x * K5_WARPS + warp, 0);
+    for (long long g = (long long)blockIdx.x * K5_WARPS + warp; g < ngroups; g += in.stride) {
+        const long long bin0 = g * 32;
+        const int nvalid = (int)((bins - bin0) < 32 ? (bins - bin0) : 32);
+        const uint16_t* myc = in.acquire(g, nvalid);
+        if (lane < nvalid) {
+            const uint16_t* row = myc + lane * K;
+            for (int s = 0; s < K; ++s) {
+                const int c = row[s];
+                double v;
+                if (direct) {
+                    v = kl_direct((double)c / dw, (double)__ldg(exp1 + s));
+                } else if (USE_LC) {
+                    v = ot[c] * (lc[c] - lw - c_log2e[s]);
+                } else {
+                    v = c > 0 ? ((double)c / dw) * (log2((double)c) - lw - c_log2e[s]) : 0.0;
+                }
+                myf[lane * K + s] = (float)v;
+                if (out64 != nullptr) out64[(bin0 + lane) * K + s] = v;
+            }
+        }
+        if (out32 != nullptr) warp_store_scores(myf, out32 + bin0 * K, nvalid, K, lane);
+        else __syncwarp();
+    }
+}
+
+// ---- S2 -----------------------------------------------------------------------------------------
+template <int KT, bool USE_LC>
+__global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
+                                                           int width, double perms, const float* __restrict__ exp2,
+                                                           const PrepFlags* __restrict__ flags, int force_direct,
+                                                           float* __restrict__ out32, double* __restrict__ out64) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint16_t* cslab = reinterpret_cast<uint16_t*>(smem_raw);                          // K5_WARPS * 2 * 32 * K u16
+    float* fslab = reinterpret_cast<float*>(smem_raw + K5_WARPS * 32 * K * 4);        // K5_WARPS * 32 * K f32
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K5_WARPS * 32 * K * 8);   // K5_WARPS * 2
+    double* lc = reinterpret_cast<double*>(bars + K5_WARPS * 2);                      // width + 1
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < K5_WARPS * 2; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    if (USE_LC)
+        for (int i = tid; i <= width; i += K5_THREADS) lc[i] = i > 0 ? log2((double)i) : 0.0;
+    __syncthreads();
+    const double lp = log2(perms);
+    const bool direct = force_direct || flags->has_zero;
+    float* myf = fslab + warp * 32 * K;
+
+    const long long ngroups = (bins + 31) / 32;
+    WarpCountStream in{cnt, {cslab + warp * 64 * K, cslab + warp * 64 * K + 32 * K}, bars + warp * 2, bins, ngroups,
+                       (long long)gridDim.x * K5_WARPS, K, lane, 0, {0u, 0u}};
+    in.issue((long long)blockIdx.x * K5_WARPS + warp, 0);
+    for (long long g = (long long)blockIdx.x * K5_WARPS + warp; g < ngroups; g += in.stride) {
+        const long long bin0 = g * 32;
+        const int nvalid = (int)((bins - bin0) < 32 ? (bins - bin0) : 32);
+        const uint16_t* myc = in.acquire(g, nvalid);
+        if (lane < nvalid) {
+            const uint16_t* row = myc + lane * K;
+            float* orow = myf + lane * K;
+            if (direct) {
+                for (int q = 0; q < K; ++q) {
+                    const long long cq = row[q];
+                    double sum = 0.0;
+                    if (cq != 0) {
+                        for (int s = 0; s < K; ++s) {
+                            const long long cs = row[s];
+                            const long long prod = (s == q) ? cs * (cs - 1) : cs * cq;
+                            if (prod != 0) sum += kl_direct((double)prod / perms, (double)__ldg(exp2 + s * K + q));
+                        }
+                    }
+                    orow[q] = (float)sum;
+                    if (out64 != nullptr) out64[(bin0 + lane) * K + q] = sum;
+                }
+            } else {
+                double cd[KT], mc[KT];
+                double a = 0.0, w = 0.0;
+#pragma unroll
+                for (int s = 0; s < KT; ++s) {
+                    const int c = s < K ? row[s] : 0;
+                    cd[s] = (double)c;
+                    const double l = USE_LC ? lc[c] : (c > 0 ? log2((double)c) : 0.0);
+                    a = fma(cd[s], l, a);
+                    w += cd[s];
+                    mc[s] = 0.0;
+                }
+#pragma unroll
+                for (int s = 0; s < KT; ++s) {
+#pragma unroll
+                    for (int q = 0; q < KT; ++q) mc[q] = fma(cd[s], c_log2e[s * KT + q], mc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < KT; ++q) {
+                    if (q < K) {
+                        const int c = row[q];
+                        double v = 0.0;
+                        if (c > 0) {
+                            const double lq = (USE_LC ? lc[c] : log2((double)c)) - lp;                   // L(c_t) - log2 P
+                            const double l1 = USE_LC ? lc[c - 1] : (c > 1 ? log2((double)(c - 1)) : 0.0);
+                            const double mqq = c_log2e[q * KT + q];
+                            double br = (a + w * lq) - mc[q];
+                            br -= cd[q] * ((lq + lq + lp) - mqq);
+                            br += (cd[q] - 1.0) * ((lq + l1) - mqq);
+                            v = (cd[q] / perms) * br;
+                        }
+                        orow[q] = (float)v;
+                        if (out64 != nullptr) out64[(bin0 + lane) * K + q] = v;
+                    }
+                }
+            }
+        }
+        if (out32 != nullptr) warp_store_scores(myf, out32 + bin0 * K, nvalid, K, lane);
+        else __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+// builds the log2 table in device scratch, copies it into constant memory (device-to-device, stream ordered)
+static int prepare_tables(const float* e, int rows, int cols, int kt, cudaStream_t st, const PrepFlags** flags_out) {
+    size_t bytes = 0;
+    uint8_t* scratch = static_cast<uint8_t*>(device_scratch(&bytes));
+    EPI_REQUIRE(scratch != nullptr, "could not allocate the per-device scratch");
+    double* table = reinterpret_cast<double*>(scratch + 64 * 8);
+    PrepFlags* flags = reinterpret_cast<PrepFlags*>(scratch + 64 * 8 + KT_MAX * KT_MAX * 8);
+    k5_prepare_kernel<<<1, 256, 0, st>>>(e, rows, cols, kt, table, flags);
+    EPI_CUDA(cudaGetLastError());
+    EPI_CUDA(cudaMemcpyToSymbolAsync(c_log2e, table, (size_t)rows * kt * 8, 0, cudaMemcpyDeviceToDevice, st));
+    *flags_out = flags;
+    return 0;
+}
+
+template <bool USE_LC>
+static int launch_s1(const uint16_t* cnt, int64_t bins, int K, int width, const float* e, const PrepFlags* flags,
+                     int direct, float* o32, double* o64, cudaStream_t st) {
+    auto kern = k5_s1_kernel<USE_LC>;
+    const size_t smem = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16 + (USE_LC ? 2 * (size_t)(width + 1) * 8 : 0);
+    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
+    kern<<<persistent_grid(ntiles, 4), K5_THREADS, smem, st>>>(cnt, bins, K, width, e, flags, direct, o32, o64);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KT, bool USE_LC>
+static int launch_s2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e,
+                     const PrepFlags* flags, int direct, float* o32, double* o64, cudaStream_t st) {
+    auto kern = k5_s2_kernel<KT, USE_LC>;
+    const size_t smem = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16 + (USE_LC ? (size_t)(width + 1) * 8 : 0);
+    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
+    kern<<<persistent_grid(ntiles, 2), K5_THREADS, smem, st>>>(cnt, bins, K, width, (double)perms, e, flags, direct,
+                                                               o32, o64);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KT>
+static int dispatch_s2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, float* o32,
+                       double* o64, int mode, cudaStream_t st) {
+    const PrepFlags* flags = nullptr;
+    if (int rc = prepare_tables(e, K, K, KT, st, &flags)) return rc;
+    const int direct = mode == EPI_SCORE_DIRECT;
+    if (width <= LC_MAX_WIDTH) return launch_s2<KT, true>(cnt, bins, K, width, perms, e, flags, direct, o32, o64, st);
+    return launch_s2<KT, false>(cnt, bins, K, width, perms, e, flags, direct, o32, o64, st);
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+static int check_score_args(const void* cnt, int64_t bins, int K, int width, const void* e, int mode) {
+    if (check_device()) return 3;
+    EPI_REQUIRE(bins >= 0 && bins < (1ll << 31), "bins=%lld out of range", (long long)bins);
+    EPI_REQUIRE(K >= 1 && K <= EPI_MAX_STATES, "num_states=%d out of range [1, %d]", K, EPI_MAX_STATES);
+    EPI_REQUIRE(width >= 1 && width <= 65535, "width=%d out of range [1, 65535]", width);
+    EPI_REQUIRE(mode == EPI_SCORE_TABLE || mode == EPI_SCORE_DIRECT, "unknown score mode %d", mode);
+    if (bins == 0) return 0;
+    EPI_REQUIRE(cnt != nullptr && e != nullptr, "null pointer argument");
+    EPI_REQUIRE((reinterpret_cast<uintptr_t>(cnt) & 15) == 0, "cnt_dev must be 16-byte aligned");
+    return 0;
+}
+
+extern "C" int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t K, int32_t width, const float* exp1_dev,
+                             float* out32_dev, double* out64_dev, int32_t mode, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_score_args(cnt_dev, bins, K, width, exp1_dev, mode)) return rc;
+    if (bins == 0 || (out32_dev == nullptr && out64_dev == nullptr)) return 0;
+    EPI_REQUIRE(out32_dev == nullptr || (reinterpret_cast<uintptr_t>(out32_dev) & 15) == 0,
+                "out32_dev must be 16-byte aligned");
+    const PrepFlags* flags = nullptr;
+    if (int rc = prepare_tables(exp1_dev, 1, K, K, st, &flags)) return rc;
+    const int direct = mode == EPI_SCORE_DIRECT;
+    if (width <= LC_MAX_WIDTH) return launch_s1<true>(cnt_dev, bins, K, width, exp1_dev, flags, direct, out32_dev, out64_dev, st);
+    return launch_s1<false>(cnt_dev, bins, K, width, exp1_dev, flags, direct, out32_dev, out64_dev, st);
+}
+
+extern "C" int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t K, int32_t width, int64_t perms,
+                             const float* exp2_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_score_args(cnt_dev, bins, K, width, exp2_dev, mode)) return rc;
+    EPI_REQUIRE(perms >= 1, "perms=%lld must be positive (needs at least 2 biosamples)", (long long)perms);
+    if (bins == 0 || (out32_dev == nullptr && out64_dev == nullptr)) return 0;
+    EPI_REQUIRE(out32_dev == nullptr || (reinterpret_cast<uintptr_t>(out32_dev) & 15) == 0,
+                "out32_dev must be 16-byte aligned");
+    if (K <= 16) return dispatch_s2<16>(cnt_dev, bins, K, width, perms, exp2_dev, out32_dev, out64_dev, mode, st);
+    if (K <= 18) return dispatch_s2<18>(cnt_dev, bins, K, width, perms, exp2_dev, out32_dev, out64_dev, mode, st);
+    return dispatch_s2<32>(cnt_dev, bins, K, width, perms, exp2_dev, out32_dev, out64_dev, mode, st);
+}

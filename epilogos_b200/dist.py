@@ -1,0 +1,49 @@
+"""torch.distributed plumbing for the stage drivers: bins are sharded across ranks (one process per GPU,
+launched with torchrun); the only exchange of the path is the all-reduce of the integer expected tables and
+the gather of per-rank score rows to the writing rank.  Without an initialised process group everything is
+a single-rank no-op.  This replaces the reference's SLURM job fan-out (run.py:193-279)."""
+import torch
+import torch.distributed as dist
+
+
+def initialised():
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size():
+    return dist.get_world_size() if initialised() else 1
+
+
+def rank():
+    return dist.get_rank() if initialised() else 0
+
+
+def all_reduce_sum(t):
+    """In-place sum over ranks of an integer table (order independent => bit-exact for any world size)."""
+    if initialised() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def gather_rows(t, total_rows, dst=0):
+    """Concatenate per-rank row blocks (ranks own consecutive row ranges) on rank `dst`; other ranks get None."""
+    if not initialised() or dist.get_world_size() == 1:
+        return t
+    ws = dist.get_world_size()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    sizes = [int(s.item()) for s in sizes]
+    assert sum(sizes) == total_rows, (sizes, total_rows)
+    maxr = max(sizes)
+    pad = torch.zeros((maxr,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(ws)] if dist.get_rank() == dst else None
+    dist.gather(pad, outs, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0)
+
+
+def barrier():
+    if initialised():
+        dist.barrier()

@@ -1,0 +1,56 @@
+"""Stage 1 -- per-file expected (background) COUNT tables.  Mirror of the reference's expected.py.
+
+    main(file1, file2, numStates, saliency, outputDir, fileTag, numProcesses, verbose)      (expected.py:11)
+
+Same arguments, same output file (`temp_exp_freq_<tag>_<file>.npy`, int64 counts, expected.py:220-223), same
+ValueError for a saliency outside 1..3 (expected.py:80-81).  Rows are sharded over the torch.distributed
+ranks (one GPU each) instead of a multiprocessing.Pool; the per-shard integer tables are summed with an
+all-reduce (expected.py:85 does np.sum over the workers' results).  `numProcesses` is accepted for signature
+compatibility: parallelism comes from the process group.
+"""
+from pathlib import Path
+from sys import argv
+from time import time
+
+import numpy as np
+
+from . import dist, helpers, session
+
+
+def main(file1, file2, numStates, saliency, outputDir, fileTag, numProcesses, verbose, backend=None):
+    tTotal = time()
+    file1Path, file2Path, outputDirPath = Path(file1), Path(file2), Path(outputDir)
+    filename = file1Path.name.split(".")[0]                                         # expected.py:31
+    if saliency not in (1, 2, 3):
+        raise ValueError("Please ensure that saliency metric is either 1, 2, or 3")
+    if saliency == 3 and str(file2) != "null":
+        raise ValueError("Please ensure that saliency metric is either 1 or 2 for Pairwise Epilogos")
+    if not verbose and dist.rank() == 0:
+        print("    {}\t".format(filename), end="", flush=True)
+
+    shard = session.load_shard(file1Path, file2Path, numStates, backend)
+    table = calculateExpected(saliency, shard, numStates, backend)
+    if dist.rank() == 0:
+        storeExpArray(table, outputDirPath, fileTag, filename)
+        print("Total Time:", time() - tTotal, flush=True) if verbose else print("\t[Done]", flush=True)
+    dist.barrier()
+
+
+def calculateExpected(saliency, shard, numStates, backend=None):
+    """Integer table of the whole file: per-rank table of the rank's rows, all-reduced (sum)."""
+    be = session.get_backend(backend)
+    if saliency in (1, 2):
+        local = be.expected_table(shard.counts(), shard.width, saliency)
+    else:
+        local = be.expected_table_s3(shard.states_device(), shard.width, numStates)
+    dist.all_reduce_sum(local)
+    return local.cpu().numpy().astype(np.int64, copy=False)
+
+
+def storeExpArray(expFreqArr, outputDirPath, fileTag, filename):
+    expFreqPath = Path(outputDirPath) / "temp_exp_freq_{}_{}.npy".format(fileTag, filename)
+    np.save(expFreqPath, expFreqArr, allow_pickle=False)
+
+
+if __name__ == "__main__":
+    main(argv[1], argv[2], int(argv[3]), int(argv[4]), argv[5], argv[6], int(argv[7]), helpers.strToBool(argv[8]))

@@ -191,3 +191,22 @@ def test_whole_genome_shape_properties(eng):
     ref = orc.s2_scores(xs, k, e2.cpu().numpy(), dtype=np.float64)
     _, s2_64 = eng.scores_s2(cnt[idx].contiguous(), cols, e2, want64=True)
     np.testing.assert_allclose(s2_64.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+# ---------------------------------------------------------- stage drivers with the CUDA provider (files)
+@pytest.mark.parametrize("saliency", [1, 2])
+def test_stage_drivers_write_reference_files(eng, golden, tmp_path, saliency):
+    """expected.main -> expectedCombination.main -> scores.main of epilogos_b200 (CUDA provider) produce the
+    reference's files: int64 temp counts, float32 exp_freq payload bit-exact, scores text (spot-diff)."""
+    from test_host_stages import run_single_pipeline
+    g = golden("real10_chr1_k18")
+    x = g["x"]
+    counts, exp, npz, text = run_single_pipeline(tmp_path, x, 18, saliency, None, gz=True)
+    assert counts.dtype == np.int64 and np.array_equal(counts, g["s%d_counts" % saliency])
+    assert exp.tobytes() == g["s%d_exp" % saliency].tobytes()
+    assert_f32_close(npz["scoreArr"], g["s%d_scores" % saliency])
+    ref_lines = g["s%d_text" % saliency].tobytes().split(b"\n")
+    got_lines = text.split(b"\n")
+    assert len(ref_lines) == len(got_lines)
+    diff = sum(a != b for a, b in zip(ref_lines, got_lines))
+    assert diff <= 2, "%d of %d text lines differ" % (diff, len(ref_lines))

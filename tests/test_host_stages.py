@@ -1,0 +1,130 @@
+"""Host-side stage drivers (epilogos_b200.expected / expectedCombination / scores) on CPU.
+
+The compute provider is replaced by tests/fake_backend.OracleBackend so that what is tested here is the host
+logic: row sharding, all-reduce of the integer tables, gather of score rows, file names / dtypes / text format
+-- at world size 1 and at world size 2 over gloo.  The CUDA provider is exercised by the -m gpu tests.
+"""
+import gzip
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def write_tsv(path, x0, chrom="chr1", gz=False):
+    opener = gzip.open if gz else open
+    with opener(path, "wt") as f:
+        for r in range(x0.shape[0]):
+            f.write("%s\t%d\t%d\t%s\n" % (chrom, r * 200, r * 200 + 200, "\t".join(str(int(v) + 1) for v in x0[r])))
+
+
+def run_single_pipeline(tmp, x, k, saliency, backend, gz=False):
+    from epilogos_b200 import expected, expectedCombination, scores, session
+    session.clear()
+    inp = tmp / "in"; out = tmp / "out"
+    inp.mkdir(exist_ok=True); out.mkdir(exist_ok=True)
+    f = inp / ("epilogos_matrix_chr1.txt" + (".gz" if gz else ""))
+    write_tsv(f, x, gz=gz)
+    tag = "in_s%d" % saliency
+    expected.main(f, "null", k, saliency, out, tag, 1, False, backend=backend)
+    temp = out / ("temp_exp_freq_%s_epilogos_matrix_chr1.npy" % tag)
+    counts = np.load(temp)
+    exp_path = out / ("exp_freq_%s.npy" % tag)
+    expectedCombination.main(out, exp_path, tag, False, backend=backend)
+    assert not temp.exists()
+    scores.main(f, "null", k, saliency, out, exp_path, tag, 1, k - 1, -1, False, backend=backend)
+    npz = np.load(out / ("temp_scores_%s_epilogos_matrix_chr1.npz" % tag), allow_pickle=True)
+    with gzip.open(out / ("scores_%s_epilogos_matrix_chr1.txt.gz" % tag), "rb") as g:
+        text = g.read()
+    return counts, np.load(exp_path), npz, text
+
+
+def test_helpers_rows_and_parse(tmp_path, golden):
+    from epilogos_b200 import helpers
+    x = golden("real10_chr1_k18")["x"][:257]
+    f = tmp_path / "m.txt.gz"
+    write_tsv(f, x, gz=True)
+    assert helpers.countRows(f) == 257
+    assert helpers.splitRows(257, 3) == [(0, 85), (85, 171), (171, 257)]
+    loc, s0 = helpers.read_matrix(f)
+    assert s0.dtype == np.int8 and np.array_equal(s0, x)
+    assert loc["chrom"][0] == "chr1" and loc["start"][5] == 1000 and loc["end"][-1] == 257 * 200
+    _, part = helpers.read_matrix(f, rows=(85, 171), want_locations=False)
+    assert np.array_equal(part, x[85:171])
+    assert helpers.strToBool("True") is True and helpers.strToBool("False") is False
+    with pytest.raises(ValueError):
+        helpers.strToBool("yes")
+
+
+@pytest.mark.parametrize("saliency", [1, 2])
+def test_single_pipeline_files_match_reference(tmp_path, golden, saliency):
+    from fake_backend import OracleBackend
+    g = golden("real10_chr1_k18")
+    x = g["x"]
+    counts, exp, npz, text = run_single_pipeline(tmp_path, x, 18, saliency, OracleBackend(), gz=(saliency == 2))
+    assert counts.dtype == np.int64 and np.array_equal(counts, g["s%d_counts" % saliency])
+    assert exp.dtype == np.float32 and exp.tobytes() == g["s%d_exp" % saliency].tobytes()
+    assert npz["scoreArr"].dtype == np.float32
+    assert npz["scoreArr"].tobytes() == g["s%d_scores" % saliency].tobytes()
+    assert str(npz["chrName"][0]) == "chr1" and npz["locationArr"].shape == (x.shape[0], 3)
+    assert text == g["s%d_text" % saliency].tobytes()
+
+
+def test_bad_saliency_raises(tmp_path):
+    from fake_backend import OracleBackend
+    from epilogos_b200 import expected
+    f = tmp_path / "m.txt"
+    write_tsv(f, np.zeros((4, 3), dtype=np.int8))
+    with pytest.raises(ValueError):
+        expected.main(f, "null", 18, 4, tmp_path, "t", 1, False, backend=OracleBackend())
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import numpy as np, torch.distributed as dist
+from pathlib import Path
+from fake_backend import OracleBackend
+from epilogos_b200 import expected, expectedCombination, scores
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+out = Path({out!r}); f = Path({f!r}); be = OracleBackend()
+for s in (1, 2):
+    tag = "in_s%d" % s
+    expected.main(f, "null", 18, s, out, tag, 1, False, backend=be)
+    expectedCombination.main(out, out / ("exp_freq_%s.npy" % tag), tag, False, backend=be)
+    scores.main(f, "null", 18, s, out, out / ("exp_freq_%s.npy" % tag), tag, 1, 17, -1, False, backend=be)
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_two_gloo_matches_single_rank(tmp_path, golden):
+    g = golden("real10_chr1_k18")
+    x = g["x"][:1001]                       # odd row count: uneven shards
+    f = tmp_path / "epilogos_matrix_chr1.txt"
+    write_tsv(f, x)
+    out = tmp_path / "out"
+    out.mkdir()
+    port = 29500 + (os.getpid() % 2000)
+    code = WORKER.format(root=str(ROOT), tests=str(ROOT / "tests"), port=port, out=str(out), f=str(f))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    logs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    from oracle import epilogos_oracle as orc
+    for s in (1, 2):
+        tag = "in_s%d" % s
+        counts = orc.s1_expected_counts(x, 18) if s == 1 else orc.s2_expected_counts(x, 18)
+        exp = np.load(out / ("exp_freq_%s.npy" % tag))
+        assert exp.tobytes() == orc.normalize_expected(counts).tobytes()
+        ref = orc.s1_scores(x, 18, exp) if s == 1 else orc.s2_scores(x, 18, exp)
+        npz = np.load(out / ("temp_scores_%s_epilogos_matrix_chr1.npz" % tag), allow_pickle=True)
+        assert npz["scoreArr"].tobytes() == ref.tobytes()
+        with gzip.open(out / ("scores_%s_epilogos_matrix_chr1.txt.gz" % tag), "rb") as gzf:
+            text = gzf.read()
+        starts = np.arange(x.shape[0]) * 200
+        assert text == orc.format_scores_text(ref, "chr1", starts, starts + 200)
