@@ -18,8 +18,8 @@ constexpr int K2_THREADS = 256;
 constexpr int K2_TILE = 512;
 constexpr int K2_TS = 6;
 
-template <int NBLK>
-__global__ void __launch_bounds__(K2_THREADS, 1)
+template <int NBLK, bool FULL>     // FULL: K == 6*NBLK, no range guards on the state index
+__global__ void __launch_bounds__(K2_THREADS, 2)
 k2_expected_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, int flush_every,
                    unsigned long long* __restrict__ n1, unsigned long long* __restrict__ n2) {
     constexpr int TS = K2_TS;
@@ -124,8 +124,8 @@ k2_expected_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, int 
 #pragma unroll
                 for (int i = 0; i < TS; ++i) {
                     const int s = bi * TS + i, q = bj * TS + i;
-                    a[i] = s < K ? row[s] : 0u;
-                    c[i] = q < K ? row[q] : 0u;
+                    a[i] = (FULL || s < K) ? row[s] : 0u;
+                    c[i] = (FULL || q < K) ? row[q] : 0u;
                 }
 #pragma unroll
                 for (int i = 0; i < TS; ++i) {
@@ -220,20 +220,26 @@ static unsigned long long* scratch_slot() {
     return b ? reinterpret_cast<unsigned long long*>(b) + (next++ & 63) : nullptr;
 }
 
-template <int NBLK>
-static int launch_k2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n1, int64_t* n2, cudaStream_t st) {
+template <int NBLK, bool FULL>
+static int launch_k2_impl(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n1, int64_t* n2, cudaStream_t st) {
     const int64_t ntiles = (bins + K2_TILE - 1) / K2_TILE;
     const size_t smem = 2 * (((size_t)K2_TILE * K * 2 + 127) & ~(size_t)127) + (size_t)(K * K + K) * 8 + 16;
-    auto kern = k2_expected_kernel<NBLK>;
+    auto kern = k2_expected_kernel<NBLK, FULL>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t flush_every = 0xffffffffll / ((int64_t)width * width);
     if (flush_every < 1) flush_every = 1;
     if (flush_every > (1 << 20)) flush_every = 1 << 20;
-    kern<<<persistent_grid(ntiles, 1), K2_THREADS, smem, st>>>(cnt, bins, K, (int)flush_every,
+    kern<<<persistent_grid(ntiles, 2), K2_THREADS, smem, st>>>(cnt, bins, K, (int)flush_every,
                                                                reinterpret_cast<unsigned long long*>(n1),
                                                                reinterpret_cast<unsigned long long*>(n2));
     EPI_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NBLK>
+static int launch_k2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n1, int64_t* n2, cudaStream_t st) {
+    if (K == NBLK * K2_TS) return launch_k2_impl<NBLK, true>(cnt, bins, K, width, n1, n2, st);
+    return launch_k2_impl<NBLK, false>(cnt, bins, K, width, n1, n2, st);
 }
 
 }  // namespace epi

@@ -30,7 +30,7 @@ constexpr int K5_WARPS = K5_THREADS / 32;
 constexpr int LC_MAX_WIDTH = 2047;        // log2(count) / count/width tables live in shared memory up to this width
 constexpr int KT_MAX = EPI_MAX_STATES;
 
-__constant__ double c_log2e[KT_MAX * KT_MAX];     // S2: log2 E[s][t], row stride KT; S1: log2 E[s]
+__constant__ __align__(16) double c_log2e[KT_MAX * KT_MAX];     // S2: log2 E[s][t], row stride KT; S1: log2 E[s]
 
 struct PrepFlags {
     int has_zero;       // some expected frequency is 0 -> masked terms -> DIRECT evaluation
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __res
                 if (direct) {
                     v = kl_direct((double)c / dw, (double)__ldg(exp1 + s));
                 } else if (USE_LC) {
-                    v = ot[c] * (lc[c] - lw - c_log2e[s]);
+                    v = c > 0 ? ot[c] * (lc[c] - lw - c_log2e[s]) : 0.0;      // absent state: +0.0 as in the reference
                 } else {
                     v = c > 0 ? ((double)c / dw) * (log2((double)c) - lw - c_log2e[s]) : 0.0;
                 }
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
         for (int i = tid; i <= width; i += K5_THREADS) lc[i] = i > 0 ? log2((double)i) : 0.0;
     __syncthreads();
     const double lp = log2(perms);
+    const double inv_perms = 1.0 / perms;
     const bool direct = force_direct || flags->has_zero;
     float* myf = fslab + warp * 32 * K;
 
@@ -220,6 +221,8 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
                     if (out64 != nullptr) out64[(bin0 + lane) * K + q] = sum;
                 }
             } else {
+                // bracket for target state t (see the header comment), after collecting terms:
+                //   br = (A - (LE c)_t) + (L(c_t) - log2 P)(W - 1) - c_t L(c_t) + (c_t - 1) L(c_t - 1) + LE_tt
                 double cd[KT], mc[KT];
                 double a = 0.0, w = 0.0;
 #pragma unroll
@@ -231,25 +234,29 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
                     w += cd[s];
                     mc[s] = 0.0;
                 }
+                const double2* le2 = reinterpret_cast<const double2*>(c_log2e);     // KT is even: 16-byte pairs
 #pragma unroll
                 for (int s = 0; s < KT; ++s) {
 #pragma unroll
-                    for (int q = 0; q < KT; ++q) mc[q] = fma(cd[s], c_log2e[s * KT + q], mc[q]);
+                    for (int q = 0; q < KT; q += 2) {
+                        const double2 m = le2[(s * KT + q) >> 1];
+                        mc[q] = fma(cd[s], m.x, mc[q]);
+                        mc[q + 1] = fma(cd[s], m.y, mc[q + 1]);
+                    }
                 }
+                const double wm1 = w - 1.0;
 #pragma unroll
                 for (int q = 0; q < KT; ++q) {
                     if (q < K) {
                         const int c = row[q];
-                        double v = 0.0;
-                        if (c > 0) {
-                            const double lq = (USE_LC ? lc[c] : log2((double)c)) - lp;                   // L(c_t) - log2 P
-                            const double l1 = USE_LC ? lc[c - 1] : (c > 1 ? log2((double)(c - 1)) : 0.0);
-                            const double mqq = c_log2e[q * KT + q];
-                            double br = (a + w * lq) - mc[q];
-                            br -= cd[q] * ((lq + lq + lp) - mqq);
-                            br += (cd[q] - 1.0) * ((lq + l1) - mqq);
-                            v = (cd[q] / perms) * br;
-                        }
+                        const int cm = c > 0 ? c - 1 : 0;
+                        const double lt = USE_LC ? lc[c] : (c > 0 ? log2((double)c) : 0.0);
+                        const double l1 = USE_LC ? lc[cm] : (cm > 0 ? log2((double)cm) : 0.0);
+                        double br = (a - mc[q]) + c_log2e[q * KT + q];
+                        br = fma(lt - lp, wm1, br);
+                        br = fma(-cd[q], lt, br);
+                        br = fma((double)cm, l1, br);
+                        const double v = c > 0 ? (cd[q] * inv_perms) * br : 0.0;   // absent state: +0.0 as in the reference
                         orow[q] = (float)v;
                         if (out64 != nullptr) out64[(bin0 + lane) * K + q] = v;
                     }

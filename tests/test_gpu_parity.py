@@ -36,6 +36,8 @@ def gpu_counts(eng, x, k):
 def assert_f32_close(got32, ref32, max_ulp_frac=2e-3):
     """float32 results equal except rounding-boundary cases (at most 1 ulp apart, and rare)."""
     got32 = np.asarray(got32); ref32 = np.asarray(ref32)
+    # zeros must carry the reference's sign ("-0.00000" vs "0.00000" in the text output)
+    assert np.array_equal(np.signbit(got32[ref32 == 0]), np.signbit(ref32[ref32 == 0]))
     neq = got32 != ref32
     if neq.any():
         a = got32[neq].astype(np.float64); b = ref32[neq].astype(np.float64)
