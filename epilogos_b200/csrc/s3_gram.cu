@@ -1,0 +1,452 @@
+// K3 -- S3 expected counts as an exact int8 one-hot Gram matrix on the 5th-generation tensor cores.
+//
+// Reference (expected.py:165-204, s3Calc): for every bin and every ORDERED pair of different biosamples
+// (i, j):  N3[i][j][x[b,i]][x[b,j]] += 1.  With the one-hot matrix OH[b][j*K+s] = (x[b,j] == s) this is
+//      G = OH^T OH   (CK x CK, int32),   N3[i][j][a][c] = G[i*K+a][j*K+c] for i != j,  0 for i == j.
+// G is symmetric, so only tiles on or above the diagonal are computed and the rest is mirrored when the
+// table is finalised (N3[j][i][c][a] = N3[i][j][a][c]).
+//
+//  * epi_s3_onehot   writes the TRANSPOSED one-hot OHT[m][b] (m = j*K+s, bins contiguous), which makes both
+//                    GEMM operands K-major (the contraction index is the bin): the canonical TN layout.
+//  * epi_s3_gram     persistent warp-specialised tcgen05 kernel: 128x256 output tiles, UMMA 128x256x32
+//                    (kind::i8, unsigned 0/1 operands, int32 accumulators in TMEM), operands streamed by TMA
+//                    (128-byte swizzle) through a 4-stage mbarrier ring; warp 0 = TMA producer, warp 1 = TMEM
+//                    allocator + single-thread MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> global tiles).
+//                    Tiles are rasterised in column groups so the ~148 tiles in flight share operand panels in L2.
+//  * epi_s3_finalize turns the (all-reduced) tile buffer into the reference's [C][C][K][K] table: int64 counts
+//                    and/or float32 frequencies (float64 divide by the grand total, expectedCombination.py:42),
+//                    mirroring the lower triangle and zeroing the i == j blocks.
+#include "common.cuh"
+
+namespace epi {
+
+constexpr int G_TM = 128;           // tile rows   (UMMA M)
+constexpr int G_TN = 256;           // tile cols   (UMMA N)
+constexpr int G_TK = 128;           // bins per pipeline stage (= one 128-byte swizzle atom of int8)
+constexpr int G_UK = 32;            // bins per tcgen05.mma (int8)
+constexpr int G_STAGES = 4;
+constexpr int G_THREADS = 192;
+constexpr int G_GROUP = 8;          // n-tiles per raster group
+constexpr int G_A_BYTES = G_TM * G_TK;          // 16 KB
+constexpr int G_B_BYTES = G_TN * G_TK;          // 32 KB
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_MAX_GROUPS = 64;
+
+struct TileSchedule {
+    int mt, nt;                       // number of 128-row / 256-col tiles
+    int ngroups;
+    int total;                        // tiles on or above the diagonal
+    int group_count[G_MAX_GROUPS];    // tiles per raster group
+};
+
+// tile (mi, nj) is needed iff some element has row <= col: mi*128 <= nj*256 + 255  <=>  mi <= 2*nj + 1
+__host__ __device__ inline int tiles_in_group(int mt, int nt, int g) {
+    const int nj0 = g * G_GROUP;
+    const int width = (nt - nj0) < G_GROUP ? (nt - nj0) : G_GROUP;
+    int count = 0;
+    for (int w = 0; w < width; ++w) {
+        const int rows = 2 * (nj0 + w) + 2;
+        count += rows < mt ? rows : mt;
+    }
+    return count;
+}
+
+// linear index within the schedule -> (mi, nj); row-major inside a group so that consecutive tiles share A rows
+__device__ inline void decode_tile(const TileSchedule& sc, int t, int& mi, int& nj) {
+    int g = 0;
+    while (g < sc.ngroups - 1 && t >= sc.group_count[g]) {
+        t -= sc.group_count[g];
+        ++g;
+    }
+    const int nj0 = g * G_GROUP;
+    const int width = (sc.nt - nj0) < G_GROUP ? (sc.nt - nj0) : G_GROUP;
+    for (int row = 0; row < sc.mt; ++row) {
+        // valid columns of this row inside the group: nj >= ceil((row - 1) / 2)
+        int first = row <= 1 ? 0 : (row - 1 + 1) / 2;
+        first = first > nj0 ? first - nj0 : 0;
+        const int valid = width - first;
+        if (valid <= 0) break;
+        if (t < valid) {
+            mi = row;
+            nj = nj0 + first + t;
+            return;
+        }
+        t -= valid;
+    }
+    mi = 0;
+    nj = nj0;      // unreachable for a consistent schedule
+}
+
+// ---- tcgen05 / TMEM wrappers --------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, issued by ONE thread
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i <- TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row atoms 1024 bytes apart.
+// (SM100 UMMA shared-memory descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout type SWIZZLE_128B = 2 [61,64).)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::i8: D=S32 (2<<4), A=U8, B=U8 (format 0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t G_IDESC = (2u << 4) | ((uint32_t)(G_TN >> 3) << 17) | ((uint32_t)(G_TM >> 4) << 24);
+
+// ================================================================================================
+// one-hot expansion, transposed:  OHT[(j*K+s)][b] = (x[b][j] == s)
+// CTA = 128 bins x 32 biosamples.  Labels are staged transposed in shared memory, then every thread
+// produces 16-byte (16-bin) segments of output rows with byte-parallel compares.
+// ================================================================================================
+constexpr int OH_BINS = 128;
+constexpr int OH_COLS = 32;
+
+__global__ void __launch_bounds__(256) s3_onehot_kernel(const int8_t* __restrict__ x, long long bins, int cols,
+                                                        long long pitch, int K, int8_t* __restrict__ oht,
+                                                        long long bp) {
+    __shared__ __align__(16) uint8_t xs[OH_COLS][OH_BINS + 16];
+    const long long b0 = (long long)blockIdx.x * OH_BINS;
+    const int j0 = blockIdx.y * OH_COLS;
+    const int tid = threadIdx.x;
+    // load [128 bins][32 cols] and transpose into xs[col][bin]; out-of-range -> 0xFF (matches no state)
+    for (int i = tid; i < OH_BINS * OH_COLS; i += 256) {
+        const int b = i / OH_COLS, j = i - b * OH_COLS;
+        uint8_t v = 0xFF;
+        if (b0 + b < bins && j0 + j < cols) v = (uint8_t)x[(b0 + b) * pitch + j0 + j];
+        xs[j][b] = v;
+    }
+    __syncthreads();
+    const int ncol = (cols - j0) < OH_COLS ? (cols - j0) : OH_COLS;
+    const int nrows = ncol * K;                       // output rows of this CTA
+    // 8 threads cover one 128-byte row segment (16 bytes each)
+    for (int r = tid >> 3; r < nrows; r += 32) {
+        const int j = r / K, s = r - j * K;
+        const int seg = tid & 7;
+        const uint4 q = *reinterpret_cast<const uint4*>(&xs[j][seg * 16]);
+        const uint32_t pat = (uint32_t)s * 0x01010101u;
+        uint4 o;
+        o.x = __vcmpeq4(q.x, pat) & 0x01010101u;
+        o.y = __vcmpeq4(q.y, pat) & 0x01010101u;
+        o.z = __vcmpeq4(q.z, pat) & 0x01010101u;
+        o.w = __vcmpeq4(q.w, pat) & 0x01010101u;
+        *reinterpret_cast<uint4*>(oht + ((long long)(j0 + j) * K + s) * bp + b0 + seg * 16) = o;
+    }
+}
+
+// ================================================================================================
+// Gram kernel
+// ================================================================================================
+__global__ void __launch_bounds__(G_THREADS, 1)
+s3_gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ TileSchedule sched, int kblocks, int accumulate, int32_t* __restrict__ tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128-byte-swizzled operand tiles need 1024-byte alignment (the launch reserves the slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ring = smem;                                                            // G_STAGES * 48 KB
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);   // TMA -> MMA
+    uint64_t* empty = full + G_STAGES;                                               // MMA -> TMA
+    uint64_t* tmem_full = empty + G_STAGES;                                          // MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 1;                                            // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);          // one arrive per epilogue warp
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, G_TN);      // 256 columns x 128 lanes of int32 accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_b);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
+                int mi, nj;
+                decode_tile(sched, t, mi, nj);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], G_STAGE_BYTES);
+                    uint8_t* st = ring + s * G_STAGE_BYTES;
+                    tma_load_2d(st, &map_a, kb * G_TK, mi * G_TM, &full[s]);
+                    tma_load_2d(st + G_A_BYTES, &map_b, kb * G_TK, nj * G_TN, &full[s]);
+                    if (++s == G_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer (one thread) ------------------------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
+                mbar_wait(tmem_empty, acc_ph ^ 1);           // epilogue has drained the previous tile
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * G_STAGE_BYTES);
+                    const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < G_TK / G_UK; ++k) {
+                        // advancing 32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+                        umma_i8(tmem_base, a_desc + 2 * k, b_desc + 2 * k, G_IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);                   // stage may be refilled once these MMAs are done
+                    if (++s == G_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma_commit(tmem_full);                       // accumulator complete
+                acc_ph ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------ epilogue: TMEM -> global tile buffer ------------------------------
+        const int quarter = warp & 3;                         // TMEM lane quarter this warp may access
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
+            mbar_wait(tmem_full, acc_ph);
+            acc_ph ^= 1;
+            tc_fence_after();
+            int32_t* dst = tiles + (long long)t * (G_TM * G_TN) + (long long)(quarter * 32 + lane) * G_TN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < G_TN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+                int4* d4 = reinterpret_cast<int4*>(dst + c0);
+                if (accumulate) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        int4 o = d4[i];
+                        o.x += (int)v[4 * i];
+                        o.y += (int)v[4 * i + 1];
+                        o.z += (int)v[4 * i + 2];
+                        o.w += (int)v[4 * i + 3];
+                        d4[i] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        d4[i] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, G_TN);
+}
+
+// ================================================================================================
+// finalise: tile buffer -> [C][C][K][K] int64 counts and / or float32 frequencies
+// one thread per output element (i, j, a, c); reads G[min][max] from the tile that holds it
+// ================================================================================================
+__global__ void __launch_bounds__(256) s3_finalize_kernel(const int32_t* __restrict__ tiles, TileSchedule sched,
+                                                          const int* __restrict__ tile_index, int cols, int K,
+                                                          double total, long long* __restrict__ counts,
+                                                          float* __restrict__ expf) {
+    const long long n = (long long)cols * cols * K * K;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % K);
+        long long r = idx / K;
+        const int a = (int)(r % K);
+        r /= K;
+        const int j = (int)(r % cols);
+        const int i = (int)(r / cols);
+        long long v = 0;
+        if (i != j) {
+            int m = i * K + a, q = j * K + c;                 // G[m][q] == G[q][m]
+            if (m > q) {
+                const int tmp = m;
+                m = q;
+                q = tmp;
+            }
+            const int mi = m / G_TM, nj = q / G_TN;
+            const int t = tile_index[mi * sched.nt + nj];
+            v = tiles[(long long)t * (G_TM * G_TN) + (long long)(m - mi * G_TM) * G_TN + (q - nj * G_TN)];
+        }
+        if (counts != nullptr) counts[idx] = v;
+        if (expf != nullptr) expf[idx] = (float)((double)v / total);
+    }
+}
+
+__global__ void s3_tile_index_kernel(TileSchedule sched, int* __restrict__ tile_index) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < sched.total; t += gridDim.x * blockDim.x) {
+        int mi, nj;
+        decode_tile(sched, t, mi, nj);
+        tile_index[mi * sched.nt + nj] = t;
+    }
+}
+
+static TileSchedule make_schedule(int64_t mp) {
+    TileSchedule sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.mt = (int)(mp / G_TM);
+    sc.nt = (int)(mp / G_TN);
+    sc.ngroups = (sc.nt + G_GROUP - 1) / G_GROUP;
+    sc.total = 0;
+    for (int g = 0; g < sc.ngroups; ++g) {
+        sc.group_count[g] = tiles_in_group(sc.mt, sc.nt, g);
+        sc.total += sc.group_count[g];
+    }
+    return sc;
+}
+
+static int make_oht_map(CUtensorMap* map, const int8_t* oht, int64_t mp, int64_t bp, int box_rows) {
+    tensor_map_encode_fn encode = get_tensor_map_encode();
+    EPI_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled entry point not available from the driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)bp, (cuuint64_t)mp};
+    const cuuint64_t gstride[1] = {(cuuint64_t)bp};
+    const cuuint32_t box[2] = {(cuuint32_t)G_TK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(oht), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EPI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (one-hot operand) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+extern "C" int epi_s3_plan(int64_t bins, int32_t cols, int32_t K, int64_t* mp, int64_t* bp, int64_t* ntiles,
+                           int64_t* onehot_bytes, int64_t* tile_bytes) {
+    EPI_REQUIRE(bins >= 0 && cols >= 1 && K >= 1 && K <= EPI_MAX_STATES, "bad S3 shape");
+    const int64_t m = (((int64_t)cols * K + G_TN - 1) / G_TN) * G_TN;
+    const int64_t b = ((bins + G_TK - 1) / G_TK) * G_TK;
+    EPI_REQUIRE(m / G_TN <= (int64_t)G_MAX_GROUPS * G_GROUP, "biosamples x states = %lld is too large for the S3 tile schedule",
+                (long long)cols * K);
+    const TileSchedule sc = make_schedule(m);
+    if (mp) *mp = m;
+    if (bp) *bp = b;
+    if (ntiles) *ntiles = sc.total;
+    if (onehot_bytes) *onehot_bytes = m * b;
+    if (tile_bytes) *tile_bytes = (int64_t)sc.total * G_TM * G_TN * 4 + (int64_t)sc.mt * sc.nt * 4;
+    return 0;
+}
+
+extern "C" int epi_s3_onehot(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t K,
+                             int8_t* oht_dev, int64_t mp, int64_t bp, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(bins >= 1 && cols >= 1 && pitch >= cols && K >= 1 && K <= EPI_MAX_STATES, "bad S3 shape");
+    EPI_REQUIRE(mp >= (int64_t)cols * K && mp % G_TN == 0 && bp >= bins && bp % G_TK == 0,
+                "mp / bp must come from epi_s3_plan");
+    EPI_REQUIRE(x_dev != nullptr && oht_dev != nullptr, "null pointer argument");
+    EPI_REQUIRE((reinterpret_cast<uintptr_t>(oht_dev) & 127) == 0, "oht_dev must be 128-byte aligned");
+    // padding rows [cols*K, mp) and padding bins are zero
+    EPI_CUDA(cudaMemsetAsync(oht_dev + (int64_t)cols * K * bp, 0, (size_t)((mp - (int64_t)cols * K) * bp), st));
+    dim3 grid((unsigned)(bp / OH_BINS), (unsigned)((cols + OH_COLS - 1) / OH_COLS));
+    s3_onehot_kernel<<<grid, 256, 0, st>>>(x_dev, bins, cols, pitch, K, oht_dev, bp);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_s3_gram(const int8_t* oht_dev, int64_t mp, int64_t bp, int32_t* tiles_dev, int32_t accumulate,
+                           void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(mp >= G_TN && mp % G_TN == 0 && bp >= G_TK && bp % G_TK == 0, "mp / bp must come from epi_s3_plan");
+    EPI_REQUIRE(bp / G_TK < (1ll << 31) && bp < (1ll << 31), "too many bins for one launch: chunk the bins");
+    EPI_REQUIRE(oht_dev != nullptr && tiles_dev != nullptr, "null pointer argument");
+    EPI_REQUIRE((reinterpret_cast<uintptr_t>(tiles_dev) & 15) == 0, "tiles_dev must be 16-byte aligned");
+    const TileSchedule sc = make_schedule(mp);
+    CUtensorMap map_a, map_b;
+    if (int rc = make_oht_map(&map_a, oht_dev, mp, bp, G_TM)) return rc;
+    if (int rc = make_oht_map(&map_b, oht_dev, mp, bp, G_TN)) return rc;
+    const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + (2 * G_STAGES + 2) * 8 + 16 + 1024;
+    EPI_CUDA(cudaFuncSetAttribute(s3_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count();
+    if (grid > sc.total) grid = sc.total;
+    s3_gram_kernel<<<grid, G_THREADS, smem, st>>>(map_a, map_b, sc, (int)(bp / G_TK), accumulate, tiles_dev);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_s3_finalize(int32_t* tiles_dev, int32_t cols, int32_t K, int64_t mp, int64_t total_bins,
+                               int64_t* counts_dev, float* exp_dev, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(cols >= 1 && K >= 1 && mp >= (int64_t)cols * K && mp % G_TN == 0, "bad S3 shape");
+    EPI_REQUIRE(tiles_dev != nullptr, "null pointer argument");
+    if (counts_dev == nullptr && exp_dev == nullptr) return 0;
+    const TileSchedule sc = make_schedule(mp);
+    // the (mi, nj) -> tile lookup lives right after the tiles in the workspace sized by epi_s3_plan
+    int* tile_index = reinterpret_cast<int*>(tiles_dev + (int64_t)sc.total * G_TM * G_TN);
+    s3_tile_index_kernel<<<(sc.total + 255) / 256, 256, 0, st>>>(sc, tile_index);
+    const double total = (double)total_bins * (double)cols * (double)(cols - 1);      // sum of the table (exact)
+    const int64_t n = (int64_t)cols * cols * K * K;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    s3_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(tiles_dev, sc, tile_index, cols, K, total,
+                                                         reinterpret_cast<long long*>(counts_dev), exp_dev);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}

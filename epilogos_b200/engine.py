@@ -140,3 +140,47 @@ def device_info():
 def counts_to_numpy(cnt):
     """CUDA int16 storage of uint16 counts -> numpy uint16."""
     return cnt.cpu().numpy().view(np.uint16)
+
+
+# ------------------------------------------------------------------------------------------------ S3
+def s3_plan(bins, cols, num_states):
+    vals = [ctypes.c_int64(0) for _ in range(5)]
+    _lib.call("epi_s3_plan", int(bins), int(cols), int(num_states), *[ctypes.byref(v) for v in vals])
+    mp, bp, ntiles, onehot_bytes, tile_bytes = [v.value for v in vals]
+    return dict(mp=mp, bp=bp, ntiles=ntiles, onehot_bytes=onehot_bytes, tile_bytes=tile_bytes)
+
+
+def s3_expected_tiles(x, cols, num_states, tiles=None, onehot_budget_bytes=24 << 30):
+    """K3.  x: CUDA int8 [bins, pitch].  Returns (tiles int32 tensor, plan): the upper-triangular 128x256 tiles of
+    the one-hot Gram matrix of this shard (the quantity that is all-reduced across ranks).  Bins are processed
+    in chunks so that the transposed one-hot workspace stays below `onehot_budget_bytes`."""
+    _require_cuda(x, torch.int8, "x")
+    bins, pitch = x.shape
+    plan = s3_plan(bins, cols, num_states)
+    mp = plan["mp"]
+    if tiles is None:
+        tiles = torch.empty(plan["tile_bytes"] // 4, dtype=torch.int32, device=x.device)
+    chunk = max(128, min(plan["bp"], (onehot_budget_bytes // mp) // 128 * 128))
+    oht = torch.empty(mp * min(chunk, plan["bp"]), dtype=torch.int8, device=x.device)
+    first = True
+    for lo in range(0, bins, chunk):
+        n = min(chunk, bins - lo)
+        bp = (n + 127) // 128 * 128
+        xs = x[lo:lo + n]
+        _lib.call("epi_s3_onehot", _ptr(xs), n, int(cols), pitch, int(num_states), _ptr(oht), mp, bp, _stream())
+        _lib.call("epi_s3_gram", _ptr(oht), mp, bp, _ptr(tiles), 0 if first else 1, _stream())
+        first = False
+    if first:      # no bins at all
+        tiles.zero_()
+    return tiles, plan
+
+
+def s3_finalize(tiles, cols, num_states, mp, total_bins, want_counts=True, want_exp=True):
+    """Tile buffer (after the all-reduce) -> (counts int64 [C,C,K,K] or None, exp float32 [C,C,K,K] or None)."""
+    _require_cuda(tiles, torch.int32, "tiles")
+    shape = (cols, cols, num_states, num_states)
+    counts = torch.empty(shape, dtype=torch.int64, device=tiles.device) if want_counts else None
+    exp = torch.empty(shape, dtype=torch.float32, device=tiles.device) if want_exp else None
+    _lib.call("epi_s3_finalize", _ptr(tiles), int(cols), int(num_states), int(mp), int(total_bins), _ptr(counts),
+              _ptr(exp), _stream())
+    return counts, exp

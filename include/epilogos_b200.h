@@ -74,6 +74,27 @@ int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int
 int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width, int64_t perms,
                   const float* exp2_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream);
 
+/* ---- K3: S3 expected counts (expected.py:165-204, s3Calc) as an int8 one-hot Gram matrix ------------
+ * N3[i][j][a][c] = #{ b : x[b][i]==a and x[b][j]==c } for i != j, 0 for i == j  (int32 per worker in the
+ * reference, int64 after np.sum).  Computed as G = OH^T OH with OH[b][j*K+s] = (x[b][j]==s) on the tensor
+ * cores (tcgen05.mma kind::i8, int32 accumulation, upper-triangular 128x256 tiles only).
+ *   epi_s3_plan      sizes: mp = padded biosamples*states, bp = padded bins, number of tiles, bytes of the
+ *                    one-hot workspace (mp*bp) and of the tile workspace (tiles + tile lookup).
+ *   epi_s3_onehot    x -> transposed one-hot OHT[mp][bp] (int8 0/1, 128-byte aligned).
+ *   epi_s3_gram      OHT -> tile buffer (int32); accumulate != 0 adds to the buffer (bin chunks).
+ *                    The tile buffer is what ranks all-reduce (integer sum) in the multi-GPU path.
+ *   epi_s3_finalize  tile buffer -> counts int64 [C][C][K][K] and/or float32 frequencies
+ *                    float(double(n) / double(total_bins*C*(C-1))) (expectedCombination.py:42); mirrors the
+ *                    lower triangle (N3[j][i][c][a] = N3[i][j][a][c]) and zeroes the i == j blocks. */
+int epi_s3_plan(int64_t bins, int32_t cols, int32_t num_states, int64_t* mp, int64_t* bp, int64_t* ntiles,
+                int64_t* onehot_bytes, int64_t* tile_bytes);
+int epi_s3_onehot(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
+                  int8_t* oht_dev, int64_t mp, int64_t bp, void* stream);
+int epi_s3_gram(const int8_t* oht_dev, int64_t mp, int64_t bp, int32_t* tiles_dev, int32_t accumulate,
+                void* stream);
+int epi_s3_finalize(int32_t* tiles_dev, int32_t cols, int32_t num_states, int64_t mp, int64_t total_bins,
+                    int64_t* counts_dev, float* exp_dev, void* stream);
+
 /* ---- whole path with HOST buffers (what expected.main -> expectedCombination.main -> scores.main
  *      compute for one in-memory matrix; run.py:196,231,246) ------------------------------------
  * x_host: int8 [bins][pitch] (any pitch >= cols; pinned memory makes the copies asynchronous).
