@@ -30,6 +30,8 @@ PROTOTYPES = {
     "epi_s3_onehot": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_int64, c_int64, c_void_p]),
     "epi_s3_gram": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
     "epi_s3_finalize": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "epi_s3_terms": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "epi_scores_s3": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "epi_single_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

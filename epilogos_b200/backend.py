@@ -41,3 +41,20 @@ class CudaBackend:
         if saliency == 1:
             return engine.scores_s1(cnt, width, exp)
         return engine.scores_s2(cnt, width, exp, perms=perms)
+
+    # -- S3 ------------------------------------------------------------------------------------------
+    def states_to_device(self, states0):
+        return engine.pack_states(states0).to(self.device, non_blocking=True)
+
+    def s3_tiles(self, x_dev, width, num_states):
+        """Upper-triangular tiles of the shard's one-hot Gram matrix (int32): the tensor that is all-reduced."""
+        return engine.s3_expected_tiles(x_dev, width, num_states)
+
+    def s3_counts(self, tiles, plan, width, num_states, total_bins):
+        counts, _ = engine.s3_finalize(tiles, width, num_states, plan["mp"], total_bins, want_counts=True,
+                                       want_exp=False)
+        return counts
+
+    def scores_s3(self, x_dev, width, num_states, exp):
+        terms = engine.s3_terms(exp.to(self.device).contiguous().reshape(-1), width, num_states)
+        return engine.scores_s3(x_dev, width, num_states, terms)

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) s3_onehot_kernel(const int8_t* __restrict
 // ================================================================================================
 __global__ void __launch_bounds__(G_THREADS, 1)
 s3_gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ TileSchedule sched, int kblocks, int accumulate, int32_t* __restrict__ tiles) {
+               const __grid_constant__ TileSchedule sched, int kblocks, int accumulate, int probe,
+               int32_t* __restrict__ tiles) {
     extern __shared__ uint8_t smem_raw[];
     // 128-byte-swizzled operand tiles need 1024-byte alignment (the launch reserves the slack)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -216,15 +217,22 @@ s3_gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_prefetch_desc(&map_b);
             int s = 0;
             uint32_t ph = 0;
+            long long issued = 0;
             for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
                 int mi, nj;
                 decode_tile(sched, t, mi, nj);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], G_STAGE_BYTES);
-                    uint8_t* st = ring + s * G_STAGE_BYTES;
-                    tma_load_2d(st, &map_a, kb * G_TK, mi * G_TM, &full[s]);
-                    tma_load_2d(st + G_A_BYTES, &map_b, kb * G_TK, nj * G_TN, &full[s]);
+                    if (probe && issued >= G_STAGES) {
+                        // tensor-peak probe: operands stay whatever is in the ring, no memory traffic at all
+                        mbar_arrive(&full[s]);
+                    } else {
+                        mbar_expect_tx(&full[s], G_STAGE_BYTES);
+                        uint8_t* st = ring + s * G_STAGE_BYTES;
+                        tma_load_2d(st, &map_a, kb * G_TK, mi * G_TM, &full[s]);
+                        tma_load_2d(st + G_A_BYTES, &map_b, kb * G_TK, nj * G_TN, &full[s]);
+                    }
+                    ++issued;
                     if (++s == G_STAGES) {
                         s = 0;
                         ph ^= 1;
@@ -424,7 +432,8 @@ extern "C" int epi_s3_gram(const int8_t* oht_dev, int64_t mp, int64_t bp, int32_
     EPI_CUDA(cudaFuncSetAttribute(s3_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count();
     if (grid > sc.total) grid = sc.total;
-    s3_gram_kernel<<<grid, G_THREADS, smem, st>>>(map_a, map_b, sc, (int)(bp / G_TK), accumulate, tiles_dev);
+    const int probe = (accumulate & 2) ? 1 : 0;      // bit 1 of `accumulate`: tensor-peak probe (results are garbage)
+    s3_gram_kernel<<<grid, G_THREADS, smem, st>>>(map_a, map_b, sc, (int)(bp / G_TK), accumulate & 1, probe, tiles_dev);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }

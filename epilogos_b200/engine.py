@@ -150,7 +150,10 @@ def s3_plan(bins, cols, num_states):
     return dict(mp=mp, bp=bp, ntiles=ntiles, onehot_bytes=onehot_bytes, tile_bytes=tile_bytes)
 
 
-def s3_expected_tiles(x, cols, num_states, tiles=None, onehot_budget_bytes=24 << 30):
+S3_CHUNK_BINS = 196608      # bins per Gram launch: keeps the ~148 tiles in flight in lock-step on their L2 panels
+
+
+def s3_expected_tiles(x, cols, num_states, tiles=None, onehot_budget_bytes=None, chunk_bins=None):
     """K3.  x: CUDA int8 [bins, pitch].  Returns (tiles int32 tensor, plan): the upper-triangular 128x256 tiles of
     the one-hot Gram matrix of this shard (the quantity that is all-reduced across ranks).  Bins are processed
     in chunks so that the transposed one-hot workspace stays below `onehot_budget_bytes`."""
@@ -160,7 +163,10 @@ def s3_expected_tiles(x, cols, num_states, tiles=None, onehot_budget_bytes=24 <<
     mp = plan["mp"]
     if tiles is None:
         tiles = torch.empty(plan["tile_bytes"] // 4, dtype=torch.int32, device=x.device)
-    chunk = max(128, min(plan["bp"], (onehot_budget_bytes // mp) // 128 * 128))
+    chunk = chunk_bins or S3_CHUNK_BINS
+    if onehot_budget_bytes is not None:
+        chunk = min(chunk, (onehot_budget_bytes // mp) // 128 * 128)
+    chunk = max(128, min(plan["bp"], chunk // 128 * 128))
     oht = torch.empty(mp * min(chunk, plan["bp"]), dtype=torch.int8, device=x.device)
     first = True
     for lo in range(0, bins, chunk):
@@ -184,3 +190,26 @@ def s3_finalize(tiles, cols, num_states, mp, total_bins, want_counts=True, want_
     _lib.call("epi_s3_finalize", _ptr(tiles), int(cols), int(num_states), int(mp), int(total_bins), _ptr(counts),
               _ptr(exp), _stream())
     return counts, exp
+
+
+def s3_terms(exp3, cols, num_states):
+    """float32 expected table [C,C,K,K] -> float64 pair terms q*log2(q/E) (scores.py:479-480)."""
+    _require_cuda(exp3, torch.float32, "exp3")
+    if exp3.numel() != cols * cols * num_states * num_states:
+        raise ValueError("expected table has %d entries, need %d" % (exp3.numel(), cols * cols * num_states ** 2))
+    terms = torch.empty(exp3.numel(), dtype=torch.float64, device=exp3.device)
+    _lib.call("epi_s3_terms", _ptr(exp3), int(cols), int(num_states), _ptr(terms), _stream())
+    return terms
+
+
+def scores_s3(x, cols, num_states, terms, want64=False, out32=None):
+    """K6.  x: CUDA int8 [bins, pitch]; terms from s3_terms()."""
+    _require_cuda(x, torch.int8, "x")
+    _require_cuda(terms, torch.float64, "terms")
+    bins, pitch = x.shape
+    if out32 is None:
+        out32 = torch.empty((bins, num_states), dtype=torch.float32, device=x.device)
+    out64 = torch.empty((bins, num_states), dtype=torch.float64, device=x.device) if want64 else None
+    _lib.call("epi_scores_s3", _ptr(x), bins, int(cols), pitch, int(num_states), _ptr(terms), _ptr(out32), _ptr(out64),
+              _stream())
+    return (out32, out64) if want64 else out32

@@ -41,10 +41,14 @@ def calculateExpected(saliency, shard, numStates, backend=None):
     be = session.get_backend(backend)
     if saliency in (1, 2):
         local = be.expected_table(shard.counts(), shard.width, saliency)
-    else:
-        local = be.expected_table_s3(shard.states_device(), shard.width, numStates)
-    dist.all_reduce_sum(local)
-    return local.cpu().numpy().astype(np.int64, copy=False)
+        dist.all_reduce_sum(local)
+        return local.cpu().numpy().astype(np.int64, copy=False)
+    # S3: the ranks all-reduce the int32 tile buffer of the one-hot Gram matrix (upper triangle only), then the
+    # [C][C][K][K] int64 table (what np.sum over the workers' int32 tables yields) is assembled
+    tiles, plan = be.s3_tiles(shard.states_device(), shard.width, numStates)
+    dist.all_reduce_sum(tiles)
+    counts = be.s3_counts(tiles, plan, shard.width, numStates, shard.total_rows)
+    return counts.cpu().numpy().astype(np.int64, copy=False)
 
 
 def storeExpArray(expFreqArr, outputDirPath, fileTag, filename):

@@ -95,6 +95,15 @@ int epi_s3_gram(const int8_t* oht_dev, int64_t mp, int64_t bp, int32_t* tiles_de
 int epi_s3_finalize(int32_t* tiles_dev, int32_t cols, int32_t num_states, int64_t mp, int64_t total_bins,
                     int64_t* counts_dev, float* exp_dev, void* stream);
 
+/* ---- K6: S3 scores (scores.py:455-506, s3Score) ---------------------------------------------------
+ * terms[i][j][a][c] = q log2(q / E3[i][j][a][c]), q = 1/(C(C-1)), 0 where E3 == 0   (scores.py:479-480)
+ * score[b][s] = sum over ordered pairs i != j with x[b][j] == s of terms[i][j][x[b][i]][x[b][j]] (:496-498)
+ * Both evaluated in float64 (the reference uses float32 and differs from exact arithmetic by its own
+ * accumulation noise); terms_dev is a caller-provided C*C*K*K float64 workspace filled by epi_s3_terms. */
+int epi_s3_terms(const float* exp3_dev, int32_t cols, int32_t num_states, double* terms_dev, void* stream);
+int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
+                  const double* terms_dev, float* out32_dev, double* out64_dev, void* stream);
+
 /* ---- whole path with HOST buffers (what expected.main -> expectedCombination.main -> scores.main
  *      compute for one in-memory matrix; run.py:196,231,246) ------------------------------------
  * x_host: int8 [bins][pitch] (any pitch >= cols; pinned memory makes the copies asynchronous).

@@ -212,3 +212,74 @@ def test_stage_drivers_write_reference_files(eng, golden, tmp_path, saliency):
     assert len(ref_lines) == len(got_lines)
     diff = sum(a != b for a, b in zip(ref_lines, got_lines))
     assert diff <= 2, "%d of %d text lines differ" % (diff, len(ref_lines))
+
+
+# ------------------------------------------------------------------------------------------------ S3
+@pytest.mark.parametrize("name", ["real10_chr1_k18", "synth_s3_c12_k15", "synth_s3_c40_k18"])
+def test_s3_expected_and_scores_match_reference_goldens(eng, golden, name):
+    g = golden(name)
+    x, k = g["x"], int(g["num_states"])
+    bins, c = x.shape
+    xd = dev_states(eng, x)
+    tiles, plan = eng.s3_expected_tiles(xd, c, k)
+    counts, exp = eng.s3_finalize(tiles, c, k, plan["mp"], bins)
+    assert counts.dtype == torch.int64 and np.array_equal(counts.cpu().numpy(), g["s3_counts"])    # tensor cores, bit-exact
+    assert exp.cpu().numpy().tobytes() == g["s3_exp"].tobytes()
+    # the [C][C][K][K] table normalised by the generic K4 path gives the same payload
+    assert eng.normalize(counts).cpu().numpy().tobytes() == g["s3_exp"].tobytes()
+    terms = eng.s3_terms(exp.reshape(-1), c, k)
+    ref_terms = orc.s3_pair_terms(c, g["s3_exp"], np.float64)
+    np.testing.assert_allclose(terms.cpu().numpy().reshape(ref_terms.shape), ref_terms, rtol=1e-13, atol=0)
+    s32, s64 = eng.scores_s3(xd, c, k, terms, want64=True)
+    sub = slice(0, 400)
+    ref64 = orc.s3_scores_f64(x[sub], k, g["s3_exp"])
+    np.testing.assert_allclose(s64.cpu().numpy()[sub], ref64, rtol=RTOL, atol=ATOL)
+    # the reference's own float32 result carries accumulation noise: agree to 2e-2 absolute
+    assert np.max(np.abs(s32.cpu().numpy() - g["s3_scores"])) < 2e-2
+
+
+def test_s3_chunked_accumulation_and_odd_sizes(eng):
+    rng = np.random.default_rng(31)
+    k, c, bins = 7, 23, 1111                        # CK = 161 -> one 256 block; bins not a multiple of 128
+    x = rng.integers(0, k, size=(bins, c)).astype(np.int8)
+    xd = dev_states(eng, x)
+    ref = orc.s3_expected_counts(x, k)
+    for chunk in (None, 128, 384):
+        tiles, plan = eng.s3_expected_tiles(xd, c, k, chunk_bins=chunk)
+        counts, exp = eng.s3_finalize(tiles, c, k, plan["mp"], bins)
+        assert np.array_equal(counts.cpu().numpy(), ref)
+        assert exp.cpu().numpy().tobytes() == orc.normalize_expected(ref).tobytes()
+    n3 = counts.cpu().numpy()
+    assert int(n3.sum()) == bins * c * (c - 1) and np.array_equal(n3, n3.transpose(1, 0, 3, 2))
+    assert not n3[np.arange(c), np.arange(c)].any()
+
+
+def test_s3_benchmark_width_matches_reference_digest(eng, golden):
+    """833 biosamples x 18 states (BASELINE config 3 width): 15104^2 Gram, 3540 tensor-core tiles."""
+    import hashlib
+    g = golden("synth_s3_c833_k18")
+    x, k = g["x"], int(g["num_states"])
+    bins, c = x.shape
+    xd = dev_states(eng, x)
+    tiles, plan = eng.s3_expected_tiles(xd, c, k)
+    counts, exp = eng.s3_finalize(tiles, c, k, plan["mp"], bins)
+    idx = torch.from_numpy(g["sample_idx"]).cuda()
+    assert np.array_equal(counts.reshape(-1)[idx].cpu().numpy(), g["counts_sample"])
+    assert np.array_equal(exp.reshape(-1)[idx].cpu().numpy(), g["exp_sample"])
+    assert int(counts.sum()) == bins * c * (c - 1)
+    assert hashlib.sha256(exp.cpu().numpy().tobytes()).digest() == g["exp_sha256"].tobytes()
+    assert hashlib.sha256(counts.cpu().numpy().tobytes()).digest() == g["counts_sha256"].tobytes()
+    terms = eng.s3_terms(exp.reshape(-1), c, k)
+    s32, s64 = eng.scores_s3(xd, c, k, terms, want64=True)
+    assert np.max(np.abs(s32.cpu().numpy() - g["s3_scores"])) < 2e-2
+    ref64 = orc.s3_scores_f64(x[:6], k, exp.cpu().numpy())
+    np.testing.assert_allclose(s64.cpu().numpy()[:6], ref64, rtol=RTOL, atol=ATOL)
+
+
+def test_s3_stage_drivers(eng, golden, tmp_path):
+    from test_host_stages import run_single_pipeline
+    g = golden("synth_s3_c12_k15")
+    counts, exp, npz, text = run_single_pipeline(tmp_path, g["x"], 15, 3, None)
+    assert counts.dtype == np.int64 and np.array_equal(counts, g["s3_counts"])
+    assert exp.tobytes() == g["s3_exp"].tobytes()
+    assert np.max(np.abs(npz["scoreArr"] - g["s3_scores"])) < 2e-2
