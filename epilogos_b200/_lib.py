@@ -5,7 +5,7 @@ CPU fallback anywhere in this package: if the library is missing, or a compute e
 without a B200, the call raises.
 """
 import ctypes
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libepilogos_b200.so"
@@ -32,6 +32,14 @@ PROTOTYPES = {
     "epi_s3_finalize": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "epi_s3_terms": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "epi_scores_s3": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "epi_shuffled_counts_perm": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64,
+                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "epi_shuffled_counts_philox": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_int32,
+                                           c_void_p, c_void_p, c_void_p]),
+    "epi_pairwise_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                     c_void_p]),
+    "epi_quiescent_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                   c_void_p]),
     "epi_single_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -58,3 +58,20 @@ class CudaBackend:
     def scores_s3(self, x_dev, width, num_states, exp):
         terms = engine.s3_terms(exp.to(self.device).contiguous().reshape(-1), width, num_states)
         return engine.scores_s3(x_dev, width, num_states, terms)
+
+    # -- paired mode -----------------------------------------------------------------------------------
+    def shuffled_counts_perm(self, states_a, states_b, perm, num_states, size_a, size_b):
+        xa, xb = self.states_to_device(states_a), self.states_to_device(states_b)
+        p = torch.as_tensor(perm.astype("int32", copy=False)).to(self.device)
+        return engine.shuffled_counts_perm(xa, states_a.shape[1], xb, states_b.shape[1], p.contiguous(), num_states,
+                                           size_a, size_b)
+
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1):
+        oa, ob = engine.shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm)
+        return (oa[0], ob[0]) if nperm == 1 else (oa, ob)
+
+    def pairwise_combine(self, score_a, score_b, null_a, null_b):
+        return engine.pairwise_combine(score_a, score_b, null_a, null_b)
+
+    def quiescent_mask(self, cnt_a, cols_a, cnt_b, cols_b, quiescent_state):
+        return engine.quiescent_mask(cnt_a, cols_a, cnt_b, cols_b, quiescent_state)

@@ -1,0 +1,249 @@
+// K7 / K8 -- paired (two-group) epilogos: shuffled-group counts, delta / null distances, quiescence mask.
+//
+// Reference: helpers.readStates paired-score branch (helpers.py:181-194) shuffles the labels of the combined
+// [A | B] row and splits them into two halves; scores.calculateScoresPairwise (scores.py:172-256) scores
+// A, B, A', B' against the shared expected table and forms
+//      delta    = score(A)  - score(B)                      (float32 - float32, scores.py:223)
+//      nullDiff = score(A') - score(B')                     (scores.py:224-225)
+//      nullDist = sum_s nullDiff^2 * sign(sum_s nullDiff)   (float32, numpy pairwise summation, scores.py:231-232)
+//      quiescent[b] = every label of A and of B equals the quiescent state (scores.py:294-303).
+// S1 and S2 scores are functions of the per-bin COUNT vector only, so a shuffle is fully described by how many
+// labels of each state land in A' and B'.
+//
+//   epi_shuffled_counts_perm    explicit permutation indices (the reference's argsort(rand) indices): used for
+//                               bit-exact parity with a seeded reference run.
+//   epi_shuffled_counts_philox  P independent uniform shuffles per bin drawn on the device: selection sampling
+//                               over the combined counts with a counter-based Philox4x32-10 stream keyed by
+//                               (seed, bin, permutation) -- results do not depend on grid shape or GPU count.
+//   epi_pairwise_combine        delta and signed squared null distance from the four float32 score arrays.
+//   epi_quiescent_mask          from the group counts: cntA[q] == C1 and cntB[q] == C2.
+#include "common.cuh"
+
+namespace epi {
+
+// ---------------------------------------------------------------- explicit permutation (test / parity mode)
+__global__ void __launch_bounds__(128) shuffled_counts_perm_kernel(
+    const int8_t* __restrict__ xa, long long pitch_a, int cols_a, const int8_t* __restrict__ xb, long long pitch_b,
+    int cols_b, const int32_t* __restrict__ perm, long long bins, int K, int size_a, int size_b,
+    uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_b) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= bins) return;
+    const int n = cols_a + cols_b;
+    unsigned short ca[EPI_MAX_STATES], cb[EPI_MAX_STATES];
+    for (int s = 0; s < EPI_MAX_STATES; ++s) ca[s] = cb[s] = 0;
+    const int32_t* p = perm + b * n;
+    for (int k = 0; k < size_a + size_b; ++k) {
+        const int idx = p[k];
+        const int v = idx < cols_a ? xa[b * pitch_a + idx] : xb[b * pitch_b + (idx - cols_a)];
+        if (k < size_a) ca[v & 31]++;
+        else cb[v & 31]++;
+    }
+    for (int s = 0; s < K; ++s) {
+        out_a[b * K + s] = ca[s];
+        out_b[b * K + s] = cb[s];
+    }
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+    uint32_t key0, key1;
+    uint32_t ctr[4];
+    uint32_t out[4];
+    int have;
+
+    __device__ __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) const {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ __forceinline__ void refill() {
+        uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+        uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+        ++ctr[0];
+        have = 4;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (have == 0) refill();
+        return out[--have];
+    }
+};
+
+// One thread per (bin, permutation).  Selection sampling: walking over the N labels of the combined row (grouped
+// by state, which is all a count-based score can see), each label goes to A' with probability needA/remaining, to
+// B' with probability needB/remaining, else it is left out (-g group sizes smaller than the groups).
+__global__ void __launch_bounds__(256) shuffled_counts_philox_kernel(
+    const uint16_t* __restrict__ cnt_a, const uint16_t* __restrict__ cnt_b, long long bins, int K, int size_a,
+    int size_b, unsigned long long seed, int nperm, uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_b) {
+    const long long total = bins * nperm;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / bins, b = idx - p * bins;        // permutation-major output [P][bins][K]
+        Philox rng;
+        rng.key0 = (uint32_t)seed;
+        rng.key1 = (uint32_t)(seed >> 32);
+        rng.ctr[0] = 0;
+        rng.ctr[1] = (uint32_t)p;
+        rng.ctr[2] = (uint32_t)b;
+        rng.ctr[3] = (uint32_t)(b >> 32);
+        rng.have = 0;
+        uint32_t remaining = 0;
+        for (int s = 0; s < K; ++s) remaining += (uint32_t)cnt_a[b * K + s] + (uint32_t)cnt_b[b * K + s];
+        uint32_t need_a = size_a, need_b = size_b;
+        for (int s = 0; s < K; ++s) {
+            const uint32_t c = (uint32_t)cnt_a[b * K + s] + (uint32_t)cnt_b[b * K + s];
+            uint32_t ga = 0, gb = 0;
+            for (uint32_t i = 0; i < c; ++i) {
+                // u uniform in [0, remaining): Lemire's multiply-shift (bias < remaining / 2^32)
+                const uint32_t u = __umulhi(rng.next(), remaining);
+                if (u < need_a) {
+                    ++ga;
+                    --need_a;
+                } else if (u < need_a + need_b) {
+                    ++gb;
+                    --need_b;
+                }
+                --remaining;
+            }
+            out_a[idx * K + s] = (uint16_t)ga;
+            out_b[idx * K + s] = (uint16_t)gb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- delta / null distance
+// numpy float32 pairwise summation of n < 128 contiguous values (what np.sum(axis=1) does per row):
+// n < 8: left to right from 0; else 8 running sums over blocks of 8, a fixed combination tree, then the tail.
+template <class F>
+__device__ __forceinline__ float numpy_rowsum_f32(int n, F at) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, at(i));
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = at(k);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], at(i + k));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, at(i));
+    return res;
+}
+
+__global__ void __launch_bounds__(256) pairwise_combine_kernel(const float* __restrict__ sa, const float* __restrict__ sb,
+                                                               const float* __restrict__ na, const float* __restrict__ nb,
+                                                               long long rows, int K, float* __restrict__ delta,
+                                                               float* __restrict__ null_dist) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        if (delta != nullptr && sa != nullptr)
+            for (int s = 0; s < K; ++s) delta[r * K + s] = __fsub_rn(sa[r * K + s], sb[r * K + s]);
+        if (null_dist != nullptr && na != nullptr) {
+            const float* pa = na + r * K;
+            const float* pb = nb + r * K;
+            const float sum = numpy_rowsum_f32(K, [&](int i) { return __fsub_rn(pa[i], pb[i]); });
+            const float sq = numpy_rowsum_f32(K, [&](int i) {
+                const float d = __fsub_rn(pa[i], pb[i]);
+                return __fmul_rn(d, d);
+            });
+            const float sign = sum > 0.f ? 1.f : (sum < 0.f ? -1.f : (sum == 0.f ? 0.f : sum));      // np.sign (nan stays nan)
+            null_dist[r] = __fmul_rn(sq, sign);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) quiescent_mask_kernel(const uint16_t* __restrict__ cnt_a,
+                                                             const uint16_t* __restrict__ cnt_b, long long bins, int K,
+                                                             int cols_a, int cols_b, int q, uint8_t* __restrict__ mask) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < bins;
+         b += (long long)gridDim.x * blockDim.x) {
+        uint8_t m = 0;
+        if (q >= 0 && q < K) m = (cnt_a[b * K + q] == cols_a && cnt_b[b * K + q] == cols_b) ? 1 : 0;
+        mask[b] = m;
+    }
+}
+
+static unsigned grid_for(long long n, int threads, int per_sm) {
+    long long blocks = (n + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+extern "C" int epi_shuffled_counts_perm(const int8_t* xa_dev, int64_t pitch_a, int32_t cols_a, const int8_t* xb_dev,
+                                        int64_t pitch_b, int32_t cols_b, const int32_t* perm_dev, int64_t bins,
+                                        int32_t K, int32_t size_a, int32_t size_b, uint16_t* cnt_a_out,
+                                        uint16_t* cnt_b_out, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(bins >= 0 && cols_a >= 1 && cols_b >= 1 && K >= 1 && K <= EPI_MAX_STATES, "bad paired shape");
+    EPI_REQUIRE(size_a >= 0 && size_b >= 0 && size_a + size_b <= cols_a + cols_b,
+                "group sizes %d + %d exceed the %d combined biosamples", size_a, size_b, cols_a + cols_b);
+    if (bins == 0) return 0;
+    EPI_REQUIRE(xa_dev && xb_dev && perm_dev && cnt_a_out && cnt_b_out, "null pointer argument");
+    shuffled_counts_perm_kernel<<<(unsigned)((bins + 127) / 128), 128, 0, st>>>(
+        xa_dev, pitch_a, cols_a, xb_dev, pitch_b, cols_b, perm_dev, bins, K, size_a, size_b, cnt_a_out, cnt_b_out);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_shuffled_counts_philox(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins,
+                                          int32_t K, int32_t size_a, int32_t size_b, uint64_t seed, int32_t nperm,
+                                          uint16_t* cnt_a_out, uint16_t* cnt_b_out, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(bins >= 0 && K >= 1 && K <= EPI_MAX_STATES && nperm >= 1, "bad paired shape");
+    EPI_REQUIRE(size_a >= 0 && size_b >= 0, "negative group size");
+    if (bins == 0) return 0;
+    EPI_REQUIRE(cnt_a_dev && cnt_b_dev && cnt_a_out && cnt_b_out, "null pointer argument");
+    shuffled_counts_philox_kernel<<<grid_for(bins * nperm, 256, 16), 256, 0, st>>>(
+        cnt_a_dev, cnt_b_dev, bins, K, size_a, size_b, (unsigned long long)seed, nperm, cnt_a_out, cnt_b_out);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_pairwise_combine(const float* score_a, const float* score_b, const float* null_a,
+                                    const float* null_b, int64_t rows, int32_t K, float* delta_out,
+                                    float* null_dist_out, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(rows >= 0 && K >= 1 && K <= EPI_MAX_STATES, "bad shape");
+    EPI_REQUIRE((delta_out == nullptr) || (score_a && score_b), "delta needs both score arrays");
+    EPI_REQUIRE((null_dist_out == nullptr) || (null_a && null_b), "null distances need both null score arrays");
+    if (rows == 0) return 0;
+    pairwise_combine_kernel<<<grid_for(rows, 256, 8), 256, 0, st>>>(score_a, score_b, null_a, null_b, rows, K, delta_out,
+                                                                    null_dist_out);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_quiescent_mask(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins, int32_t K,
+                                  int32_t cols_a, int32_t cols_b, int32_t quiescent_state, uint8_t* mask_out,
+                                  void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(bins >= 0 && K >= 1 && K <= EPI_MAX_STATES, "bad shape");
+    if (bins == 0) return 0;
+    EPI_REQUIRE(cnt_a_dev && cnt_b_dev && mask_out, "null pointer argument");
+    quiescent_mask_kernel<<<grid_for(bins, 256, 8), 256, 0, st>>>(cnt_a_dev, cnt_b_dev, bins, K, cols_a, cols_b,
+                                                                  quiescent_state, mask_out);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}

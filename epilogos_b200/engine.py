@@ -213,3 +213,50 @@ def scores_s3(x, cols, num_states, terms, want64=False, out32=None):
     _lib.call("epi_scores_s3", _ptr(x), bins, int(cols), pitch, int(num_states), _ptr(terms), _ptr(out32), _ptr(out64),
               _stream())
     return (out32, out64) if want64 else out32
+
+
+# ------------------------------------------------------------------------------------------------ paired
+def shuffled_counts_perm(xa, cols_a, xb, cols_b, perm, num_states, size_a, size_b):
+    """Counts of the shuffled halves A', B' for explicit permutation indices (int32 [bins, cols_a+cols_b])."""
+    _require_cuda(xa, torch.int8, "xa")
+    _require_cuda(xb, torch.int8, "xb")
+    _require_cuda(perm, torch.int32, "perm")
+    bins = xa.shape[0]
+    ca = torch.empty((bins, num_states), dtype=torch.int16, device=xa.device)
+    cb = torch.empty((bins, num_states), dtype=torch.int16, device=xa.device)
+    _lib.call("epi_shuffled_counts_perm", _ptr(xa), xa.shape[1], int(cols_a), _ptr(xb), xb.shape[1], int(cols_b),
+              _ptr(perm), bins, int(num_states), int(size_a), int(size_b), _ptr(ca), _ptr(cb), _stream())
+    return ca, cb
+
+
+def shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm=1):
+    """nperm uniform shuffles per bin drawn on the device; returns int16 tensors [nperm, bins, K]."""
+    _require_cuda(cnt_a, torch.int16, "cnt_a")
+    _require_cuda(cnt_b, torch.int16, "cnt_b")
+    bins, k = cnt_a.shape
+    oa = torch.empty((nperm, bins, k), dtype=torch.int16, device=cnt_a.device)
+    ob = torch.empty((nperm, bins, k), dtype=torch.int16, device=cnt_a.device)
+    _lib.call("epi_shuffled_counts_philox", _ptr(cnt_a), _ptr(cnt_b), bins, k, int(size_a), int(size_b),
+              ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(nperm), _ptr(oa), _ptr(ob), _stream())
+    return oa, ob
+
+
+def pairwise_combine(score_a=None, score_b=None, null_a=None, null_b=None):
+    """(delta float32 [rows, K] or None, null_dist float32 [rows] or None)."""
+    ref = score_a if score_a is not None else null_a
+    rows, k = ref.shape
+    delta = torch.empty((rows, k), dtype=torch.float32, device=ref.device) if score_a is not None else None
+    dist = torch.empty(rows, dtype=torch.float32, device=ref.device) if null_a is not None else None
+    _lib.call("epi_pairwise_combine", _ptr(score_a), _ptr(score_b), _ptr(null_a), _ptr(null_b), rows, k, _ptr(delta),
+              _ptr(dist), _stream())
+    return delta, dist
+
+
+def quiescent_mask(cnt_a, cols_a, cnt_b, cols_b, quiescent_state):
+    _require_cuda(cnt_a, torch.int16, "cnt_a")
+    _require_cuda(cnt_b, torch.int16, "cnt_b")
+    bins, k = cnt_a.shape
+    mask = torch.empty(bins, dtype=torch.uint8, device=cnt_a.device)
+    _lib.call("epi_quiescent_mask", _ptr(cnt_a), _ptr(cnt_b), bins, k, int(cols_a), int(cols_b), int(quiescent_state),
+              _ptr(mask), _stream())
+    return mask

@@ -104,6 +104,33 @@ int epi_s3_terms(const float* exp3_dev, int32_t cols, int32_t num_states, double
 int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
                   const double* terms_dev, float* out32_dev, double* out64_dev, void* stream);
 
+/* ---- K7 / K8: paired (two-group) epilogos ------------------------------------------------------------
+ * S1/S2 scores depend on a group only through its per-bin count vector, so the paired path is:
+ * epi_bin_counts on A and on B; shuffled-group counts (below); epi_scores_s1/s2 on the four count arrays
+ * against the expected table of the union [A | B] (helpers.py:173-179); epi_pairwise_combine.
+ *   epi_shuffled_counts_perm    counts of A' = first size_a and B' = next size_b labels of the combined row
+ *                               permuted by perm[b][0..cols_a+cols_b) (helpers.py:183-194; size = group widths,
+ *                               or -g for both).  Bit-exact replay of a seeded reference run.
+ *   epi_shuffled_counts_philox  nperm independent uniform shuffles per bin, drawn on the device from the
+ *                               group counts (Philox4x32-10 keyed by seed, bin, permutation);
+ *                               outputs are [nperm][bins][K].  The reference draws exactly one.
+ *   epi_pairwise_combine        delta = score_a - score_b (float32, scores.py:223); null_dist =
+ *                               sum_s d^2 * sign(sum_s d), d = null_a - null_b, float32 with numpy's pairwise
+ *                               summation order (scores.py:224-232).  Either output (with its inputs) may be NULL.
+ *   epi_quiescent_mask          1 where every label of both groups equals quiescent_state (scores.py:294-303);
+ *                               all 0 for quiescent_state == -1. */
+int epi_shuffled_counts_perm(const int8_t* xa_dev, int64_t pitch_a, int32_t cols_a, const int8_t* xb_dev,
+                             int64_t pitch_b, int32_t cols_b, const int32_t* perm_dev, int64_t bins,
+                             int32_t num_states, int32_t size_a, int32_t size_b, uint16_t* cnt_a_out,
+                             uint16_t* cnt_b_out, void* stream);
+int epi_shuffled_counts_philox(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins,
+                               int32_t num_states, int32_t size_a, int32_t size_b, uint64_t seed, int32_t nperm,
+                               uint16_t* cnt_a_out, uint16_t* cnt_b_out, void* stream);
+int epi_pairwise_combine(const float* score_a, const float* score_b, const float* null_a, const float* null_b,
+                         int64_t rows, int32_t num_states, float* delta_out, float* null_dist_out, void* stream);
+int epi_quiescent_mask(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins, int32_t num_states,
+                       int32_t cols_a, int32_t cols_b, int32_t quiescent_state, uint8_t* mask_out, void* stream);
+
 /* ---- whole path with HOST buffers (what expected.main -> expectedCombination.main -> scores.main
  *      compute for one in-memory matrix; run.py:196,231,246) ------------------------------------
  * x_host: int8 [bins][pitch] (any pitch >= cols; pinned memory makes the copies asynchronous).

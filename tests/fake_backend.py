@@ -36,3 +36,26 @@ class OracleBackend:
         if saliency == 1:
             return torch.from_numpy(orc.s1_scores_from_counts(c, width, exp.numpy()))
         return torch.from_numpy(orc.s2_scores_from_counts(c, perms or width * (width - 1), exp.numpy()))
+
+    # paired mode
+    def shuffled_counts_perm(self, states_a, states_b, perm, num_states, size_a, size_b):
+        gs = -1 if (size_a, size_b) == (states_a.shape[1], states_b.shape[1]) else size_a
+        sa, sb = orc.paired_split(states_a, states_b, perm, gs)
+        return self.counts(sa, num_states), self.counts(sb, num_states)
+
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1):
+        raise NotImplementedError("the test double only replays explicit permutations")
+
+    def pairwise_combine(self, score_a, score_b, null_a, null_b):
+        delta = None if score_a is None else score_a - score_b
+        dist = None
+        if null_a is not None:
+            d = (null_a - null_b).numpy()
+            dist = torch.from_numpy(np.sum(np.square(d), axis=1) * np.sign(np.sum(d, axis=1)))
+        return delta, dist
+
+    def quiescent_mask(self, cnt_a, cols_a, cnt_b, cols_b, q):
+        a, b = self._cnt(cnt_a), self._cnt(cnt_b)
+        if q == -1:
+            return torch.zeros(a.shape[0], dtype=torch.uint8)
+        return torch.from_numpy(((a[:, q] == cols_a) & (b[:, q] == cols_b)).astype(np.uint8))

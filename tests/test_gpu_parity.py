@@ -283,3 +283,82 @@ def test_s3_stage_drivers(eng, golden, tmp_path):
     assert counts.dtype == np.int64 and np.array_equal(counts, g["s3_counts"])
     assert exp.tobytes() == g["s3_exp"].tobytes()
     assert np.max(np.abs(npz["scoreArr"] - g["s3_scores"])) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ paired
+@pytest.mark.parametrize("k", [5, 8, 15, 18, 25])
+def test_pairwise_combine_is_bitwise_numpy(eng, k):
+    """delta and signed squared null distance reproduce numpy's float32 arithmetic and pairwise summation order
+    (scores.py:223-232) bit for bit."""
+    rng = np.random.default_rng(k)
+    a, b, c, d = [(rng.standard_normal((3000, k)) * rng.choice([1e-3, 1.0, 30.0], size=(3000, 1))).astype(np.float32)
+                  for _ in range(4)]
+    c[:5] = d[:5]                                             # exact zeros -> sign 0
+    delta, dist = eng.pairwise_combine(*[torch.from_numpy(t).cuda() for t in (a, b, c, d)])
+    nd = c - d
+    ref = np.sum(np.square(nd), axis=1) * np.sign(np.sum(nd, axis=1))
+    assert delta.cpu().numpy().tobytes() == (a - b).tobytes()
+    assert dist.cpu().numpy().tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("name", ["paired_real10_k18", "paired_synth_c30_c25_k18", "paired_synth_g20_k18",
+                                  "paired_synth_q0_k18"])
+def test_paired_stage_driver_replays_seeded_reference(eng, golden, tmp_path, name):
+    from test_host_stages import run_paired_pipeline
+    g = golden(name)
+    for s in (1, 2):
+        if "s%d_counts" % s not in g.files:
+            continue
+        sub = tmp_path / ("s%d" % s)
+        sub.mkdir()
+        counts, exp, null, quies, text = run_paired_pipeline(sub, g["xa"], g["xb"], int(g["num_states"]), s, None,
+                                                             int(g["seed"]), int(g["group_size"]),
+                                                             int(g["quiescent_state"]))
+        assert np.array_equal(counts, g["s%d_counts" % s]) and exp.tobytes() == g["s%d_exp" % s].tobytes()
+        assert np.array_equal(quies, g["s%d_quiescence" % s])
+        ref_null = g["s%d_null" % s]
+        np.testing.assert_allclose(null, ref_null, rtol=2e-5, atol=1e-9)
+        assert (null == ref_null).mean() > 0.98
+        ref_lines = g["s%d_delta_text" % s].tobytes().split(b"\n")
+        got_lines = text.split(b"\n")
+        assert len(ref_lines) == len(got_lines)
+        assert sum(x != y for x, y in zip(ref_lines, got_lines)) <= 3
+
+
+def test_device_shuffle_is_a_uniform_split(eng):
+    """Philox selection sampling: exact group sizes, never more than available, hypergeometric means, keyed by
+    (seed, bin, permutation) only."""
+    rng = np.random.default_rng(3)
+    k, c1, c2, bins, nperm = 18, 40, 33, 600, 64
+    xa = rng.integers(0, k, size=(bins, c1)).astype(np.int8)
+    xb = rng.integers(0, 6, size=(bins, c2)).astype(np.int8)
+    ca = eng.bin_counts(dev_states(eng, xa), c1, k)
+    cb = eng.bin_counts(dev_states(eng, xb), c2, k)
+    oa, ob = eng.shuffled_counts_philox(ca, cb, c1, c2, seed=99, nperm=nperm)
+    oa_n, ob_n = eng.counts_to_numpy(oa).astype(np.int64), eng.counts_to_numpy(ob).astype(np.int64)
+    comb = (eng.counts_to_numpy(ca).astype(np.int64) + eng.counts_to_numpy(cb).astype(np.int64))[None]
+    assert (oa_n.sum(-1) == c1).all() and (ob_n.sum(-1) == c2).all()
+    assert ((oa_n + ob_n) == comb).all()                       # full-size groups: every label lands somewhere
+    mean = oa_n.mean(axis=0)                                    # E[a'_s] = c1 * c_s / N
+    expect = c1 * comb[0] / (c1 + c2)
+    assert np.abs(mean - expect).max() < 1.5                    # sd of the mean ~ 0.35 at 64 permutations
+    again, _ = eng.shuffled_counts_philox(ca, cb, c1, c2, seed=99, nperm=8)
+    assert torch.equal(again, oa[:8])
+    other, _ = eng.shuffled_counts_philox(ca, cb, c1, c2, seed=100, nperm=8)
+    assert not torch.equal(other, oa[:8])
+    # -g style sub-groups: sizes respected, leftovers unassigned
+    ga, gb = eng.shuffled_counts_philox(ca, cb, 20, 20, seed=5, nperm=4)
+    ga_n, gb_n = eng.counts_to_numpy(ga).astype(np.int64), eng.counts_to_numpy(gb).astype(np.int64)
+    assert (ga_n.sum(-1) == 20).all() and (gb_n.sum(-1) == 20).all() and ((ga_n + gb_n) <= comb).all()
+
+
+def test_paired_stage_driver_device_null(eng, golden, tmp_path):
+    """Default (device-drawn) null: same delta / quiescence files, null distances with the right distribution."""
+    from test_host_stages import run_paired_pipeline
+    g = golden("paired_synth_c30_c25_k18")
+    counts, exp, null, quies, text = run_paired_pipeline(tmp_path, g["xa"], g["xb"], 18, 1, None, 0, null_mode="device")
+    assert np.array_equal(quies, g["s1_quiescence"])
+    ref = g["s1_null"]
+    assert null.shape == ref.shape and null.dtype == np.float32
+    qs = [0.1, 0.25, 0.5, 0.75, 0.9]
+    assert np.abs(np.quantile(null, qs) - np.quantile(ref, qs)).max() < 0.35 * np.std(ref)

@@ -128,3 +128,48 @@ def test_world_size_two_gloo_matches_single_rank(tmp_path, golden):
             text = gzf.read()
         starts = np.arange(x.shape[0]) * 200
         assert text == orc.format_scores_text(ref, "chr1", starts, starts + 200)
+
+
+def run_paired_pipeline(tmp, xa, xb, k, saliency, backend, seed, group_size=-1, quiescent=None, null_mode="reference"):
+    from epilogos_b200 import expected, expectedCombination, scores, session
+    session.clear()
+    a = tmp / "a"; b = tmp / "b"; out = tmp / "out"
+    for d in (a, b, out):
+        d.mkdir(exist_ok=True)
+    fa, fb = a / "epilogos_matrix_chr1.txt", b / "epilogos_matrix_chr1.txt"
+    write_tsv(fa, xa); write_tsv(fb, xb)
+    tag = "a_b_s%d" % saliency
+    expected.main(fa, fb, k, saliency, out, tag, 1, False, backend=backend)
+    counts = np.load(out / ("temp_exp_freq_%s_epilogos_matrix_chr1.npy" % tag))
+    exp_path = out / ("exp_freq_%s.npy" % tag)
+    expectedCombination.main(out, exp_path, tag, False, backend=backend)
+    os.environ["EPILOGOS_B200_NULL"] = null_mode
+    np.random.seed(seed)
+    try:
+        scores.main(fa, fb, k, saliency, out, exp_path, tag, 1, k - 1 if quiescent is None else quiescent, group_size,
+                    False, backend=backend)
+    finally:
+        os.environ.pop("EPILOGOS_B200_NULL", None)
+    null = np.load(out / ("temp_nullDistances_%s_epilogos_matrix_chr1.npz" % tag))["nullDistances"]
+    quies = np.load(out / ("temp_quiescence_%s_epilogos_matrix_chr1.npz" % tag))["quiescenceArr"]
+    with gzip.open(out / ("pairwiseDelta_%s_epilogos_matrix_chr1.txt.gz" % tag), "rb") as g:
+        text = g.read()
+    return counts, np.load(exp_path), null, quies, text
+
+
+@pytest.mark.parametrize("name", ["paired_real10_k18", "paired_synth_g20_k18", "paired_synth_q0_k18"])
+def test_paired_pipeline_files_match_reference(tmp_path, golden, name):
+    from fake_backend import OracleBackend
+    g = golden(name)
+    for s in (1, 2):
+        if "s%d_counts" % s not in g.files:
+            continue
+        sub = tmp_path / ("s%d" % s)
+        sub.mkdir()
+        counts, exp, null, quies, text = run_paired_pipeline(sub, g["xa"], g["xb"], int(g["num_states"]), s,
+                                                             OracleBackend(), int(g["seed"]), int(g["group_size"]),
+                                                             int(g["quiescent_state"]))
+        assert np.array_equal(counts, g["s%d_counts" % s]) and exp.tobytes() == g["s%d_exp" % s].tobytes()
+        assert null.dtype == np.float32 and null.tobytes() == g["s%d_null" % s].tobytes()
+        assert quies.dtype == np.bool_ and np.array_equal(quies, g["s%d_quiescence" % s])
+        assert text == g["s%d_delta_text" % s].tobytes()

@@ -15,7 +15,8 @@ ap.add_argument("--bins", type=int, default=1_250_000)
 ap.add_argument("--cols", type=int, default=833)
 ap.add_argument("--states", type=int, default=18)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--chunk", type=int, default=196608)
+ap.add_argument("--chunk", type=int, default=131072)
+ap.add_argument("--score-bins", type=int, default=65536)
 a = ap.parse_args()
 
 x = synth.synth_states_device(a.bins, a.cols, a.states, seed=3)
@@ -49,6 +50,12 @@ t_probe = ev(lambda: _lib.call("epi_s3_gram", p(oht), mp, cb, p(tiles), 2, st))
 t_oh = ev(lambda: _lib.call("epi_s3_onehot", p(x), a.bins, a.cols, x.shape[1], a.states, p(oht), mp, bp, st))
 t_gram = ev(lambda: _lib.call("epi_s3_gram", p(oht), mp, bp, p(tiles), 0, st))
 t_fin = ev(lambda: engine.s3_finalize(tiles, a.cols, a.states, mp, a.bins, want_counts=False, want_exp=True))
+_, exp3 = engine.s3_finalize(tiles, a.cols, a.states, mp, a.bins, want_counts=False, want_exp=True)
+t_terms = ev(lambda: engine.s3_terms(exp3.reshape(-1), a.cols, a.states))
+terms = engine.s3_terms(exp3.reshape(-1), a.cols, a.states)
+xs = x[: a.score_bins]
+so = torch.empty((xs.shape[0], a.states), dtype=torch.float32, device="cuda")
+t_score = ev(lambda: engine.scores_s3(xs, a.cols, a.states, terms, out32=so))
 ck = a.cols * a.states
 useful = a.bins * ck * (ck + 1)                      # upper triangle incl. diagonal, 2 ops per MAC
 issued = plan["ntiles"] * 128 * 256 * 2 * bp          # what the tensor cores actually execute
@@ -56,5 +63,6 @@ print(json.dumps({"shape": vars(a), "plan": plan, "onehot_ms": t_oh, "gram_ms": 
                   "useful_TOPS": useful / (t_gram * 1e-3) / 1e12, "issued_TOPS": issued / (t_gram * 1e-3) / 1e12,
                   "chunked_expected_ms": t_chunked, "chunked_useful_TOPS": useful / (t_chunked * 1e-3) / 1e12,
                   "probe_ms": t_probe, "probe_issued_TOPS": plan["ntiles"] * 128 * 256 * 2 * cb / (t_probe * 1e-3) / 1e12,
-                  "onehot_GBps": mp * bp / (t_oh * 1e-3) / 1e9,
+                  "terms_ms": t_terms, "score_ms_for_score_bins": t_score, "score_bins_per_s": xs.shape[0] / (t_score * 1e-3),
+                  "score_lookups_per_s": xs.shape[0] * a.cols * (a.cols - 1) / (t_score * 1e-3), "onehot_GBps": mp * bp / (t_oh * 1e-3) / 1e9,
                   "bins_per_s_expected": a.bins / ((t_oh + t_gram + t_fin) * 1e-3)}))
