@@ -33,6 +33,7 @@ CONFIGS = {
     "s2_genome_833": (GENOME_BINS, 833, 18, "S2 whole-genome 15.5M bins x 833 biosamples, 18-state (BASELINE configs[1])"),
     "s2_genome_127": (GENOME_BINS, 127, 15, "S2 whole-genome 15.5M bins x 127 biosamples, 15-state (BASELINE configs[4])"),
     "s1_chr1_833": (1_246_253, 833, 18, "S1 chr1 1,246,253 bins x 833 biosamples, 18-state (shape of BASELINE configs[0])"),
+    "s3_chr1_833": (1_250_000, 833, 18, "S3 chr1 1.25M bins x 833 biosamples, 18-state (BASELINE configs[2])"),
 }
 
 
@@ -129,7 +130,11 @@ def run_reference(args):
     if rank != 0:
         return
     bins, cols, k, desc = CONFIGS[args.config]
-    saliency = 1 if args.config.startswith("s1") else 2
+    saliency = int(args.config[1])
+    if saliency == 3:
+        print(json.dumps({"impl": "reference", "unavailable": "S3 row-loop port needs ~1 s per bin at 833 biosamples; "
+                          "see profiles/ for the sampled figure"}), flush=True)
+        return
     base, sec = cpu_baseline(cols, k, saliency, budget_s=6.0, steps=max(1, args.steps), warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "bins/sec for expected+scores (S%d)" % saliency, "value": base["value"],
@@ -210,8 +215,10 @@ def run_ours(args):
     bins, cols, k, desc = CONFIGS[args.config]
     if args.bins:
         bins = args.bins
-    saliency = 1 if args.config.startswith("s1") else 2
+    saliency = int(args.config[1])
     engine.device_info()
+    if saliency == 3:
+        return run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, desc)
 
     x = synth.synth_states_device(bins, cols, k, seed=1234 + rank, kind=args.kind)
     cnt = torch.empty((bins, k), dtype=torch.int16, device="cuda")
@@ -325,6 +332,84 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_baseline(cols, k, saliency)
             line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, desc):
+    """S3 (BASELINE configs[2]): one-hot expansion + tcgen05 int8 Gram (chunked) + finalise + pair terms + scores.
+    Parity-test configuration; reported with the tensor-pipe roofline of the Gram kernel."""
+    import torch
+    if args.bins:
+        bins = args.bins
+    x = synth.synth_states_device(bins, cols, k, seed=4321 + rank, kind=args.kind)
+    plan = engine.s3_plan(bins, cols, k)
+    tiles = torch.empty(plan["tile_bytes"] // 4, dtype=torch.int32, device="cuda")
+    scores = torch.empty((bins, k), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    gram_ev = []
+
+    def step(timed):
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        engine.s3_expected_tiles(x, cols, k, tiles=tiles)
+        if timed:
+            e1.record(stream)
+            gram_ev.append((e0, e1))
+        if world > 1:
+            dist.all_reduce(tiles)
+        _, exp3 = engine.s3_finalize(tiles, cols, k, plan["mp"], bins * world, want_counts=False, want_exp=True)
+        terms = engine.s3_terms(exp3.reshape(-1), cols, k)
+        engine.scores_s3(x, cols, k, terms, out32=scores)
+
+    steps = min(args.steps, 3)
+    step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(steps):
+        step(True)
+    t1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([t0.elapsed_time(t1) / steps, sum(a.elapsed_time(b) for a, b in gram_ev) / len(gram_ev)],
+                      device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step, gram_ms = float(ms[0]), float(ms[1])
+    if rank == 0:
+        ck = cols * k
+        useful = bins * ck * (ck + 1)
+        peak_tops = 4500.0
+        pf = ROOT / "profiles" / "int8_tensor_peak.json"
+        src = "datasheet dense int8 4.5 POP/s (B200)"
+        if pf.exists():
+            try:
+                peak_tops = float(json.loads(pf.read_text())["probe_issued_TOPS"])
+                src = "measured: same kernel with operand loads disabled (profiles/int8_tensor_peak.json)"
+            except Exception:
+                pass
+        line = {
+            "metric": "bins/sec for expected+scores (S3)", "value": bins * world / (ms_per_step * 1e-3), "unit": "bins/s",
+            "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (tensor), f64 scores", "data": "synthetic",
+            "config": {"workload": desc, "bins_per_gpu": bins, "biosamples": cols, "states": k, "saliency": 3,
+                       "distribution": args.kind, "l2": "one-hot operand panels streamed per 131072-bin chunk"},
+            "roofline": {"bound": "tensor", "kernel": "s3_onehot_kernel + s3_gram_kernel (chunked)",
+                         "achieved": useful / (gram_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "TOP/s",
+                         "frac": useful / (gram_ms * 1e-3) / 1e12 / peak_tops, "traffic": None, "peak_source": src,
+                         "algorithmic_ops_per_launch": useful, "ms_per_launch": gram_ms},
+            "e2e": None, "gpu_launches": steps * (2 * ((bins + engine.S3_CHUNK_BINS - 1) // engine.S3_CHUNK_BINS) + 4),
+            "clocks": clocks,
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

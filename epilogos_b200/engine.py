@@ -104,9 +104,14 @@ def scores_s2(cnt, width, exp2, perms=None, want64=False, mode=EPI_SCORE_TABLE, 
     return (out32, out64) if want64 else out32
 
 
-def single_host(x_host, cols, num_states, saliency, want_scores=True):
+_pinned_scores = {}
+
+
+def single_host(x_host, cols, num_states, saliency, want_scores=True, scores_out=None):
     """Whole S1/S2 path on a HOST matrix (numpy int8 [bins, pitch] or a pinned torch int8 tensor).
-    Returns (counts int64 ndarray, exp float32 ndarray, scores float32 ndarray or None)."""
+    Returns (counts int64 ndarray, exp float32 ndarray, scores float32 ndarray or None).  `scores_out` may be a
+    pinned float32 torch tensor [bins, K] to receive the scores; otherwise one pinned buffer per shape is kept and
+    reused (the returned array aliases it until the next call with the same shape)."""
     if isinstance(x_host, torch.Tensor):
         if x_host.is_cuda or x_host.dtype != torch.int8 or not x_host.is_contiguous():
             raise TypeError("x_host must be a contiguous CPU int8 tensor")
@@ -122,10 +127,16 @@ def single_host(x_host, cols, num_states, saliency, want_scores=True):
     scores = None
     sp = ctypes.c_void_p(0)
     if want_scores:
-        scores_t = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
-        scores = scores_t.numpy()
-        sp = ctypes.c_void_p(scores_t.data_ptr())
-        single_host._keep = scores_t
+        if scores_out is None:
+            key = (bins, num_states)
+            if key not in _pinned_scores:
+                _pinned_scores.clear()
+                _pinned_scores[key] = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
+            scores_out = _pinned_scores[key]
+        if scores_out.dtype != torch.float32 or tuple(scores_out.shape) != (bins, num_states):
+            raise TypeError("scores_out must be a float32 tensor of shape [bins, K]")
+        scores = scores_out.numpy()
+        sp = ctypes.c_void_p(scores_out.data_ptr())
     _lib.call("epi_single_host", xp, bins, int(cols), pitch, int(num_states), int(saliency),
               ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(exp.ctypes.data), sp)
     return counts, exp, scores
@@ -150,7 +161,7 @@ def s3_plan(bins, cols, num_states):
     return dict(mp=mp, bp=bp, ntiles=ntiles, onehot_bytes=onehot_bytes, tile_bytes=tile_bytes)
 
 
-S3_CHUNK_BINS = 196608      # bins per Gram launch: keeps the ~148 tiles in flight in lock-step on their L2 panels
+S3_CHUNK_BINS = 131072      # bins per Gram launch: keeps the ~148 tiles in flight in lock-step on their L2 panels
 
 
 def s3_expected_tiles(x, cols, num_states, tiles=None, onehot_budget_bytes=None, chunk_bins=None):
