@@ -40,6 +40,11 @@ PROTOTYPES = {
                                      c_void_p]),
     "epi_quiescent_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p]),
+    "epi_tsv_shape": (c_int, [c_char_p, POINTER(c_int64), POINTER(c_int32)]),
+    "epi_pack_tsv": (c_int, [c_char_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
+    "epi_write_scores_gz": (c_int, [c_char_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                    c_int32, c_int32]),
     "epi_single_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

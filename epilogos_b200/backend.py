@@ -5,6 +5,7 @@ CUDA device, and it raises if the library or a B200 is missing -- there is no CP
 drivers take the backend as a parameter only so that the CPU-only unit tests can exercise the
 sharding / all-reduce / gather / file-naming logic with a stand-in defined under tests/.
 """
+import numpy as np
 import torch
 
 from . import engine
@@ -20,9 +21,22 @@ class CudaBackend:
         engine.device_info()
 
     # -- per-bin counts of a shard (numpy int8 [rows, C], 0-based) -> device tensor [rows, K] (uint16 in int16)
+    def _upload(self, states0):
+        """numpy int8 [rows, C] -> device [rows, pitch].  Matrices that come from helpers.read_matrix are views of an
+        already pitched (and possibly pinned) buffer and are uploaded as they are."""
+        base = getattr(states0, "base", None)
+        if (isinstance(base, np.ndarray) and base.dtype == np.int8 and base.ndim == 2 and base.flags.c_contiguous
+                and base.shape[0] == states0.shape[0] and base.shape[1] % 16 == 0 and base.shape[1] >= states0.shape[1]
+                and (states0.size == 0 or states0.ctypes.data == base.ctypes.data)):
+            return torch.from_numpy(base).to(self.device, non_blocking=True)
+        return engine.pack_states(states0).to(self.device, non_blocking=True)
+
     def counts(self, states0, num_states):
-        x = engine.pack_states(states0).to(self.device, non_blocking=True)
-        return engine.bin_counts(x, states0.shape[1], num_states)
+        return engine.bin_counts(self._upload(states0), states0.shape[1], num_states)
+
+    def add_counts(self, cnt_a, cnt_b):
+        """Counts of the concatenated matrix [A | B] (helpers.py:173-179) = sum of the group counts."""
+        return (cnt_a + cnt_b).contiguous()
 
     # -- integer expected table of the shard: int64 [K] (S1) or [K, K] (S2), on the device
     def expected_table(self, cnt, width, saliency):
@@ -44,7 +58,7 @@ class CudaBackend:
 
     # -- S3 ------------------------------------------------------------------------------------------
     def states_to_device(self, states0):
-        return engine.pack_states(states0).to(self.device, non_blocking=True)
+        return self._upload(states0)
 
     def s3_tiles(self, x_dev, width, num_states):
         """Upper-triangular tiles of the shard's one-hot Gram matrix (int32): the tensor that is all-reduced."""

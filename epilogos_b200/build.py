@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("epilogos_b200: nvcc compilation failed")
     link = [NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + \
-        [str(o) for o in objs]
+        [str(o) for o in objs] + ["-lz"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("epilogos_b200: link failed:\n" + r.stdout)

@@ -1,4 +1,6 @@
 // K2 (S1/S2 expected count tables from the per-bin counts) and K4 (normalise).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace epi {
@@ -229,7 +231,7 @@ static int launch_k2_impl(const uint16_t* cnt, int64_t bins, int K, int width, i
     int64_t flush_every = 0xffffffffll / ((int64_t)width * width);
     if (flush_every < 1) flush_every = 1;
     if (flush_every > (1 << 20)) flush_every = 1 << 20;
-    kern<<<persistent_grid(ntiles, 2), K2_THREADS, smem, st>>>(cnt, bins, K, (int)flush_every,
+    kern<<<persistent_grid(ntiles, getenv("EPI_K2_CTAS") ? atoi(getenv("EPI_K2_CTAS")) : 2), K2_THREADS, smem, st>>>(cnt, bins, K, (int)flush_every,
                                                                reinterpret_cast<unsigned long long*>(n1),
                                                                reinterpret_cast<unsigned long long*>(n2));
     EPI_CUDA(cudaGetLastError());

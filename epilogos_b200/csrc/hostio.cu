@@ -1,0 +1,414 @@
+// Host-side I/O of the scoring path: the callers and data formats either side of
+// the kernels.  Pure host code (compiled by nvcc for convenience, links zlib).
+//
+//   epi_tsv_shape        rows (newline count, helpers.countRows helpers.py:80-99) and columns of the first line
+//   epi_pack_tsv         rows [lo, hi) of `chr start end s_1 .. s_C` -> int8 labels-1 in the kernels' pitched
+//                        layout + start/end/chromosome per row (replaces the pandas parse of helpers.readStates,
+//                        helpers.py:150-168, and of scores.py:161); labels are validated here
+//   epi_write_scores_gz  `chr \t start \t end \t K x "%.5f"` lines through gzip (scores.writeScores,
+//                        scores.py:509-536): rows are formatted and deflated in parallel as independent gzip
+//                        members (a valid multi-member .gz; the decompressed text is byte-identical to the
+//                        reference's)
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace epi {
+
+struct Reader {
+    gzFile gz = nullptr;       // gzopen reads plain files transparently as well
+    std::vector<char> buf;
+    size_t pos = 0, len = 0;
+    bool eof = false;
+
+    bool open(const char* path) {
+        gz = gzopen(path, "rb");
+        if (!gz) return false;
+        gzbuffer(gz, 1 << 20);
+        buf.resize(8 << 20);
+        return true;
+    }
+    bool fill() {
+        if (eof) return false;
+        const int n = gzread(gz, buf.data(), (unsigned)buf.size());
+        if (n <= 0) {
+            eof = true;
+            len = pos = 0;
+            return false;
+        }
+        len = (size_t)n;
+        pos = 0;
+        return true;
+    }
+    // next byte or -1
+    inline int get() {
+        if (pos == len && !fill()) return -1;
+        return (unsigned char)buf[pos++];
+    }
+    ~Reader() {
+        if (gz) gzclose(gz);
+    }
+};
+
+// "%.5f" of a double with printf semantics (round-half-even on the exact binary value).  Fast path: scale by 1e5 and
+// round; whenever the scaled value is within 1e-6 of a rounding boundary (or huge / non-finite) defer to snprintf.
+static inline char* format_5f(char* p, double d) {
+    if (!(fabs(d) < 1e9)) return p + sprintf(p, "%.5f", d);
+    const bool neg = signbit(d);
+    const double a = fabs(d) * 1e5;
+    const double fl = floor(a);
+    const double frac = a - fl;
+    if (fabs(frac - 0.5) < 1e-6) return p + sprintf(p, "%.5f", d);
+    unsigned long long q = (unsigned long long)fl + (frac > 0.5 ? 1ull : 0ull);
+    if (neg) *p++ = '-';
+    const unsigned long long ip = q / 100000ull;
+    unsigned fr = (unsigned)(q % 100000ull);
+    char tmp[24];
+    int n = 0;
+    unsigned long long v = ip;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    *p++ = '.';
+    p[4] = (char)('0' + fr % 10); fr /= 10;
+    p[3] = (char)('0' + fr % 10); fr /= 10;
+    p[2] = (char)('0' + fr % 10); fr /= 10;
+    p[1] = (char)('0' + fr % 10); fr /= 10;
+    p[0] = (char)('0' + fr % 10);
+    return p + 5;
+}
+
+static inline char* format_i64(char* p, long long v) {
+    if (v < 0) {
+        *p++ = '-';
+        v = -v;
+    }
+    char tmp[24];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out) {
+    EPI_REQUIRE(path != nullptr, "null path");
+    Reader rd;
+    EPI_REQUIRE(rd.open(path), "cannot open %s", path);
+    int64_t rows = 0;
+    int32_t tabs_first = 0;
+    bool first = true;
+    while (rd.fill()) {
+        const char* b = rd.buf.data();
+        const size_t n = rd.len;
+        size_t i = 0;
+        if (first) {
+            for (; i < n; ++i) {
+                if (b[i] == '\t') ++tabs_first;
+                else if (b[i] == '\n') {
+                    first = false;
+                    break;
+                }
+            }
+        }
+        for (; i < n; ++i) rows += (b[i] == '\n');
+    }
+    if (rows_out) *rows_out = rows;
+    if (cols_out) *cols_out = tabs_first + 1 - 3;           // biosample columns (after chr, start, end)
+    return 0;
+}
+
+// Line source: a background thread inflates the file into a ring of large blocks while the caller parses the
+// previous one; lines that straddle a block boundary are stitched into a side buffer.
+struct LineSource {
+    static constexpr size_t BLOCK = 16u << 20;
+    gzFile gz = nullptr;
+    std::vector<char> blocks[2];
+    size_t lens[2] = {0, 0};
+    std::thread worker;
+    std::atomic<int> ready[2];          // 1 = filled by the worker, 0 = free
+    std::atomic<bool> done{false};
+    int cur = 0;
+    size_t pos = 0;
+    std::vector<char> carry;
+
+    bool open(const char* path) {
+        gz = gzopen(path, "rb");
+        if (!gz) return false;
+        gzbuffer(gz, 1 << 20);
+        blocks[0].resize(BLOCK);
+        blocks[1].resize(BLOCK);
+        ready[0] = ready[1] = 0;
+        worker = std::thread([this]() {
+            int w = 0;
+            for (;;) {
+                while (ready[w].load(std::memory_order_acquire) != 0) std::this_thread::yield();
+                const int n = gzread(gz, blocks[w].data(), (unsigned)BLOCK);
+                lens[w] = n > 0 ? (size_t)n : 0;
+                const bool last = n <= 0;
+                if (last) done.store(true, std::memory_order_release);
+                ready[w].store(1, std::memory_order_release);
+                if (last) break;
+                w ^= 1;
+            }
+        });
+        while (ready[0].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        return true;
+    }
+    // advance to the next block; false at end of file
+    bool next_block() {
+        ready[cur].store(0, std::memory_order_release);
+        if (lens[cur] == 0) return false;
+        cur ^= 1;
+        while (ready[cur].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        pos = 0;
+        return lens[cur] != 0;
+    }
+    // next line [begin, end) without the newline; returns false at end of file.  has_nl tells whether the line was
+    // terminated (the reference counts newline characters, helpers.py:92-97).
+    bool next_line(const char*& begin, const char*& end, bool& has_nl) {
+        for (;;) {
+            const char* base = blocks[cur].data();
+            const size_t len = lens[cur];
+            if (pos < len) {
+                const char* nl = static_cast<const char*>(memchr(base + pos, '\n', len - pos));
+                if (nl != nullptr && carry.empty()) {
+                    begin = base + pos;
+                    end = nl;
+                    pos = (size_t)(nl - base) + 1;
+                    has_nl = true;
+                    return true;
+                }
+                if (nl != nullptr) {
+                    carry.insert(carry.end(), base + pos, nl);
+                    pos = (size_t)(nl - base) + 1;
+                    line_buf.swap(carry);
+                    carry.clear();
+                    begin = line_buf.data();
+                    end = line_buf.data() + line_buf.size();
+                    has_nl = true;
+                    return true;
+                }
+                carry.insert(carry.end(), base + pos, base + len);
+                pos = len;
+            }
+            if (!next_block()) {
+                if (carry.empty()) return false;
+                line_buf.swap(carry);
+                carry.clear();
+                begin = line_buf.data();
+                end = line_buf.data() + line_buf.size();
+                has_nl = false;
+                return true;
+            }
+        }
+    }
+    std::vector<char> line_buf;
+    ~LineSource() {
+        // let the worker finish: mark both blocks free until it reports the end of the stream
+        if (worker.joinable()) {
+            while (!done.load(std::memory_order_acquire)) {
+                ready[0].store(0, std::memory_order_release);
+                ready[1].store(0, std::memory_order_release);
+                std::this_thread::yield();
+            }
+            worker.join();
+        }
+        if (gz) gzclose(gz);
+    }
+};
+
+extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states,
+                            int8_t* out, int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id,
+                            char* chrom_names, int32_t chrom_names_cap, int32_t* n_chrom_out) {
+    EPI_REQUIRE(path != nullptr && (out != nullptr || row_hi == row_lo), "null pointer argument");
+    EPI_REQUIRE(row_lo >= 0 && row_hi >= row_lo && cols >= 1 && pitch >= cols, "bad row range / shape");
+    EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
+    LineSource src;
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    std::vector<std::string> names;
+    const char *p, *e;
+    bool has_nl;
+    int64_t row = 0;
+    for (; row < row_lo; ++row)
+        EPI_REQUIRE(src.next_line(p, e, has_nl), "%s has only %lld rows, wanted rows from %lld", path, (long long)row,
+                    (long long)row_lo);
+    int last_id = -1;
+    for (; row < row_hi; ++row) {
+        EPI_REQUIRE(src.next_line(p, e, has_nl), "%s ends after %lld rows, wanted rows up to %lld", path, (long long)row,
+                    (long long)row_hi);
+        if (e > p && e[-1] == '\r') --e;
+        const int64_t r = row - row_lo;
+        // ---- chromosome name ----
+        const char* t = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
+        EPI_REQUIRE(t != nullptr, "%s: row %lld is truncated (expected chr<TAB>start<TAB>end<TAB>states)", path,
+                    (long long)row);
+        if (chrom_id != nullptr) {
+            const size_t nl = (size_t)(t - p);
+            int id = -1;
+            if (last_id >= 0 && names[last_id].size() == nl && memcmp(names[last_id].data(), p, nl) == 0) id = last_id;
+            for (size_t i = 0; id < 0 && i < names.size(); ++i)
+                if (names[i].size() == nl && memcmp(names[i].data(), p, nl) == 0) id = (int)i;
+            if (id < 0) {
+                id = (int)names.size();
+                names.emplace_back(p, nl);
+            }
+            chrom_id[r] = last_id = id;
+        }
+        p = t + 1;
+        // ---- start, end ----
+        for (int f = 0; f < 2; ++f) {
+            long long v = 0;
+            bool negv = false;
+            if (p < e && *p == '-') {
+                negv = true;
+                ++p;
+            }
+            const char* d0 = p;
+            while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+            EPI_REQUIRE(p > d0 && p < e && *p == '\t', "%s: row %lld: bad coordinate field", path, (long long)row);
+            ++p;
+            if (f == 0 && starts) starts[r] = negv ? -v : v;
+            if (f == 1 && ends) ends[r] = negv ? -v : v;
+        }
+        // ---- state labels: 1..num_states, one to three digits ----
+        int8_t* dst = out + r * pitch;
+        int j = 0;
+        while (j < cols) {
+            EPI_REQUIRE(p < e, "%s: row %lld has %d state columns, expected %d", path, (long long)row, j, cols);
+            unsigned v = (unsigned)(*p - '0');
+            EPI_REQUIRE(v <= 9, "%s: row %lld column %d: state label is not an integer", path, (long long)row, j + 4);
+            ++p;
+            while (p < e && (unsigned)(*p - '0') <= 9) {
+                v = v * 10 + (unsigned)(*p++ - '0');
+                EPI_REQUIRE(v <= 1000, "%s: row %lld column %d: state label out of range", path, (long long)row, j + 4);
+            }
+            EPI_REQUIRE(v >= 1 && v <= (unsigned)num_states, "%s: row %lld column %d: state %u outside 1..%d", path,
+                        (long long)row, j + 4, v, num_states);
+            dst[j++] = (int8_t)(v - 1);
+            if (p < e) {
+                EPI_REQUIRE(*p == '\t', "%s: row %lld column %d: unexpected character", path, (long long)row, j + 3);
+                ++p;
+                EPI_REQUIRE(j < cols || p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
+            }
+        }
+        EPI_REQUIRE(p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
+        for (int64_t jj = cols; jj < pitch; ++jj) dst[jj] = 0;
+    }
+    if (n_chrom_out) *n_chrom_out = (int32_t)names.size();
+    if (chrom_names != nullptr) {
+        size_t off = 0;
+        for (const std::string& s : names) {
+            EPI_REQUIRE(off + s.size() + 1 <= (size_t)chrom_names_cap, "chromosome name buffer too small");
+            memcpy(chrom_names + off, s.c_str(), s.size() + 1);
+            off += s.size() + 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int epi_write_scores_gz(const char* path, const char* chrom_names, const int32_t* chrom_id,
+                                   const int64_t* starts, const int64_t* ends, const float* scores, int64_t rows,
+                                   int32_t K, int32_t level, int32_t threads) {
+    EPI_REQUIRE(path && chrom_names && starts && ends && (scores || rows == 0), "null pointer argument");
+    EPI_REQUIRE(rows >= 0 && K >= 1, "bad shape");
+    if (level < 0 || level > 9) level = 6;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    std::vector<const char*> names;
+    {
+        int max_id = 0;
+        for (int64_t r = 0; r < rows && chrom_id; ++r) max_id = std::max(max_id, (int)chrom_id[r]);
+        const char* p = chrom_names;
+        for (int i = 0; i <= max_id; ++i) {
+            names.push_back(p);
+            p += strlen(p) + 1;
+        }
+    }
+    const int64_t block = 16384;
+    const int64_t nblocks = (rows + block - 1) / block;
+    std::vector<std::vector<unsigned char>> outs((size_t)nblocks);
+    std::atomic<int64_t> next(0);
+    std::atomic<int> failed(0);
+    auto work = [&]() {
+        std::vector<char> text;
+        for (;;) {
+            const int64_t bi = next.fetch_add(1);
+            if (bi >= nblocks) break;
+            const int64_t lo = bi * block, hi = std::min(rows, lo + block);
+            text.resize((size_t)(hi - lo) * (64 + (size_t)K * 28));
+            char* p = text.data();
+            for (int64_t r = lo; r < hi; ++r) {
+                const char* nm = names[chrom_id ? chrom_id[r] : 0];
+                const size_t nl = strlen(nm);
+                memcpy(p, nm, nl);
+                p += nl;
+                *p++ = '\t';
+                p = format_i64(p, starts[r]);
+                *p++ = '\t';
+                p = format_i64(p, ends[r]);
+                const float* row = scores + r * K;
+                for (int s = 0; s < K; ++s) {
+                    *p++ = '\t';
+                    p = format_5f(p, (double)row[s]);
+                }
+                *p++ = '\n';
+            }
+            const size_t tlen = (size_t)(p - text.data());
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {     // +16: gzip member
+                failed = 1;
+                break;
+            }
+            std::vector<unsigned char>& o = outs[(size_t)bi];
+            o.resize(deflateBound(&zs, (uLong)tlen) + 64);
+            zs.next_in = reinterpret_cast<Bytef*>(text.data());
+            zs.avail_in = (uInt)tlen;
+            zs.next_out = o.data();
+            zs.avail_out = (uInt)o.size();
+            const int rc = deflate(&zs, Z_FINISH);
+            o.resize(zs.total_out);
+            deflateEnd(&zs);
+            if (rc != Z_STREAM_END) {
+                failed = 1;
+                break;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    const int nthreads = (int)std::min<int64_t>(threads, std::max<int64_t>(nblocks, 1));
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    EPI_REQUIRE(!failed, "zlib deflate failed while writing %s", path);
+    FILE* f = fopen(path, "wb");
+    EPI_REQUIRE(f != nullptr, "cannot open %s for writing", path);
+    bool ok = true;
+    if (nblocks == 0) {
+        // an empty gzip member so that the file is a valid .gz holding no text
+        static const unsigned char empty_gz[20] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        ok = fwrite(empty_gz, 1, sizeof(empty_gz), f) == sizeof(empty_gz);
+    }
+    for (auto& o : outs) ok = ok && (fwrite(o.data(), 1, o.size(), f) == o.size());
+    ok = (fclose(f) == 0) && ok;
+    EPI_REQUIRE(ok, "short write to %s", path);
+    return 0;
+}

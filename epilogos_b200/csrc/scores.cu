@@ -21,6 +21,8 @@
 //
 // I/O is staged per warp (no block-wide barriers in the steady state): 32 bins of counts come in as 16-byte
 // vectors, 32 rows of float32 scores leave as 16-byte vectors.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace epi {
@@ -271,6 +273,11 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int k5_ctas_per_sm(int dflt) {
+    if (const char* e = getenv("EPI_K5_CTAS")) return atoi(e) > 0 ? atoi(e) : dflt;      // tuning knob
+    return dflt;
+}
+
 // builds the log2 table in device scratch, copies it into constant memory (device-to-device, stream ordered)
 static int prepare_tables(const float* e, int rows, int cols, int kt, cudaStream_t st, const PrepFlags** flags_out) {
     size_t bytes = 0;
@@ -292,7 +299,7 @@ static int launch_s1(const uint16_t* cnt, int64_t bins, int K, int width, const 
     const size_t smem = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16 + (USE_LC ? 2 * (size_t)(width + 1) * 8 : 0);
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
-    kern<<<persistent_grid(ntiles, 4), K5_THREADS, smem, st>>>(cnt, bins, K, width, e, flags, direct, o32, o64);
+    kern<<<persistent_grid(ntiles, k5_ctas_per_sm(4)), K5_THREADS, smem, st>>>(cnt, bins, K, width, e, flags, direct, o32, o64);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -304,7 +311,7 @@ static int launch_s2(const uint16_t* cnt, int64_t bins, int K, int width, int64_
     const size_t smem = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16 + (USE_LC ? (size_t)(width + 1) * 8 : 0);
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
-    kern<<<persistent_grid(ntiles, 2), K5_THREADS, smem, st>>>(cnt, bins, K, width, (double)perms, e, flags, direct,
+    kern<<<persistent_grid(ntiles, k5_ctas_per_sm(3)), K5_THREADS, smem, st>>>(cnt, bins, K, width, (double)perms, e, flags, direct,
                                                                o32, o64);
     EPI_CUDA(cudaGetLastError());
     return 0;

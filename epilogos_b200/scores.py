@@ -66,7 +66,7 @@ def _gather_locations(shard):
     td.gather_object(shard.loc, parts, dst=0)
     if dist.rank() != 0:
         return None
-    return {k: np.concatenate([p[k] for p in parts]) for k in ("chrom", "start", "end")}
+    return {k: np.concatenate([p[k] for p in parts]) for k in ("chrom", "start", "end")}   # ids are per-rank: dropped
 
 
 if __name__ == "__main__":

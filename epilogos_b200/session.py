@@ -33,10 +33,12 @@ class Shard:
         self.total_rows = helpers.countRows(file1)
         self.lo, self.hi = helpers.splitRows(self.total_rows, dist.world_size())[dist.rank()]
         rows = (self.lo, self.hi)
-        self.loc, self.states_a = helpers.read_matrix(file1, rows, want_locations=True)
+        pinned = getattr(self.backend, "name", "") == "cuda"
+        self.loc, self.states_a = helpers.read_matrix(file1, rows, want_locations=True, num_states=num_states,
+                                                      pinned=pinned)
         self.states_b = None
         if str(file2) != "null":
-            _, self.states_b = helpers.read_matrix(file2, rows, want_locations=False)
+            _, self.states_b = helpers.read_matrix(file2, rows, want_locations=False, num_states=num_states)
             if self.states_b.shape[0] != self.states_a.shape[0]:
                 raise ValueError("paired input files must have the same number of rows")
         self._counts = {}
@@ -56,9 +58,13 @@ class Shard:
         return self.states_a if not self.paired else np.concatenate((self.states_a, self.states_b), axis=1)
 
     def counts(self, which="all"):
+        """Per-bin counts of the whole matrix ("all": the union [A | B] in paired mode) or of one group."""
         if which not in self._counts:
-            m = {"all": self.combined, "a": lambda: self.states_a, "b": lambda: self.states_b}[which]()
-            self._counts[which] = self.backend.counts(m, self.num_states)
+            if which == "all" and self.paired:
+                self._counts[which] = self.backend.add_counts(self.counts("a"), self.counts("b"))
+            else:
+                m = self.states_b if which == "b" else self.states_a
+                self._counts[which] = self.backend.counts(m, self.num_states)
         return self._counts[which]
 
     def states_device(self):

@@ -1,25 +1,31 @@
 """Text / npz writers of the score stage (scores.py:509-536, 163-169)."""
-import gzip
+import ctypes
 
 import numpy as np
 
+from . import _lib
 
-def write_scores_text(path, scores32, loc):
-    """`chr \\t start \\t end \\t K x "{:.5f}"` per bin through gzip (scores.py:530-536).  The reference formats
-    np.float32 values with "{:.5f}", i.e. the exact binary value rounded to 5 decimals -- identical to
-    "%.5f" % float(v)."""
-    scores32 = np.asarray(scores32, dtype=np.float32)
+
+def write_scores_text(path, scores32, loc, level=6, threads=0):
+    """`chr \\t start \\t end \\t K x "{:.5f}"` per bin through gzip (scores.py:530-536), formatted and compressed by
+    the native writer (epi_write_scores_gz).  The reference formats np.float32 values with "{:.5f}", i.e. the exact
+    binary value rounded to 5 decimals, which is what printf's "%.5f" of the widened double gives."""
+    scores32 = np.ascontiguousarray(scores32, dtype=np.float32)
     rows, k = scores32.shape
-    fmt = "\t".join(["%.5f"] * k)
-    chrom, start, end = loc["chrom"], loc["start"], loc["end"]
-    with gzip.open(path, "wt") as out:
-        step = 65536
-        for lo in range(0, rows, step):
-            hi = min(rows, lo + step)
-            block = scores32[lo:hi].astype(np.float64)
-            lines = ["%s\t%d\t%d\t%s\n" % (chrom[i], start[i], end[i], fmt % tuple(block[i - lo]))
-                     for i in range(lo, hi)]
-            out.write("".join(lines))
+    if "chrom_id" in loc:
+        cid = np.ascontiguousarray(loc["chrom_id"], dtype=np.int32)
+        names = loc["chrom_names"]
+    else:
+        uniq, cid = np.unique(np.asarray(loc["chrom"], dtype=object).astype(str), return_inverse=True)
+        cid = cid.astype(np.int32)
+        names = b"\0".join(u.encode() for u in uniq) + b"\0"
+    if rows == 0:
+        names = names or b"\0"
+    starts = np.ascontiguousarray(loc["start"], dtype=np.int64)
+    ends = np.ascontiguousarray(loc["end"], dtype=np.int64)
+    _lib.call("epi_write_scores_gz", str(path).encode(), ctypes.c_char_p(names), ctypes.c_void_p(cid.ctypes.data),
+              ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
+              ctypes.c_void_p(scores32.ctypes.data), rows, k, int(level), int(threads))
 
 
 def location_array(loc):

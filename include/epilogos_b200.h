@@ -140,6 +140,23 @@ int epi_quiescent_mask(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int
 int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
                     int32_t saliency, int64_t* counts_host, float* exp_host, float* scores_host);
 
+/* ---- host-side I/O either side of the kernels (no GPU needed) -------------------------------------
+ * epi_tsv_shape       rows = number of newline characters (helpers.countRows, helpers.py:80-99), cols = biosample
+ *                     columns of the first line (fields - 3).  Plain or gzip files.
+ * epi_pack_tsv        rows [row_lo, row_hi) of `chr start end s_1 .. s_C` (README.md:286-292) -> int8 labels-1 into
+ *                     out[row][pitch] (pad bytes zeroed), start/end per row, chromosome ids per row plus the distinct
+ *                     names as consecutive NUL-terminated strings.  Replaces the pandas parse of helpers.readStates
+ *                     (helpers.py:150-168) and of scores.py:161.  Labels outside 1..num_states are an error.
+ * epi_write_scores_gz `chr\tstart\tend\t` + K x "%.5f" per row through gzip (scores.writeScores, scores.py:509-536);
+ *                     decompressed text is byte-identical to the reference's.  level 0-9 (else 6), threads <= 0 = all. */
+int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
+int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states, int8_t* out,
+                 int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id, char* chrom_names,
+                 int32_t chrom_names_cap, int32_t* n_chrom_out);
+int epi_write_scores_gz(const char* path, const char* chrom_names, const int32_t* chrom_id, const int64_t* starts,
+                        const int64_t* ends, const float* scores, int64_t rows, int32_t num_states, int32_t level,
+                        int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,9 @@ class OracleBackend:
     def _cnt(cnt):
         return cnt.numpy().view(np.uint16).astype(np.int64)
 
+    def add_counts(self, cnt_a, cnt_b):
+        return cnt_a + cnt_b
+
     def expected_table(self, cnt, width, saliency):
         c = self._cnt(cnt)
         if saliency == 1:
