@@ -45,6 +45,8 @@ PROTOTYPES = {
                              c_void_p, c_void_p, c_int32, POINTER(c_int32)]),
     "epi_write_scores_gz": (c_int, [c_char_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     c_int32, c_int32]),
+    "epi_roi_maxmean": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, POINTER(c_int32)]),
     "epi_single_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -157,6 +157,16 @@ int epi_write_scores_gz(const char* path, const char* chrom_names, const int32_t
                         const int64_t* ends, const float* scores, int64_t rows, int32_t num_states, int32_t level,
                         int32_t threads);
 
+/* ---- region-of-interest selection over the per-bin score sums (host code) ---------------------------
+ * helpers.maxMean (helpers.py:253-274) -> filter_regions maxmean (filter_regions.py:375-448): centered rolling
+ * max / mean over `window` bins, windows over two chromosomes dropped, ranked by (max, mean, score) descending,
+ * greedy non-overlapping pick of at most max_regions.  Outputs are in the order helpers.maxMean returns them
+ * (out arrays sized max_regions): index of the window's centre row, window start / end coordinates, RollingMax,
+ * RollingMean. */
+int epi_roi_maxmean(const double* score, const int64_t* starts, const int64_t* ends, int64_t n, int32_t window,
+                    int32_t max_regions, int64_t* out_original_idx, int64_t* out_start, int64_t* out_end,
+                    double* out_rolling_max, double* out_rolling_mean, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

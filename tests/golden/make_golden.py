@@ -83,6 +83,43 @@ def s3_big_case(name, bins=48, cols=833, k=18, seed=11):
     print("wrote", name)
 
 
+def roi_cases():
+    """helpers.maxMean of the reference (the ROI selector that consumes the single-mode scores) on
+    (a) S1 scores of a 200 000-bin real-data slice, window 50, and (b) two short synthetic chromosomes with odd /
+    even windows.  Scores are the oracle's (bit-identical to the reference's, see test_oracle_golden)."""
+    import warnings
+    ref._import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos.helpers import maxMean
+    x = real_slice(100000, 200000)
+    exp, scores = orc.expected_and_scores(x, 18, 1)
+    n = len(scores)
+    loc = np.empty((n, 3), dtype=object)
+    loc[:, 0] = "chr1"; loc[:, 1] = np.arange(n) * 200; loc[:, 2] = np.arange(n) * 200 + 200
+    rois, idx = maxMean(np.concatenate((loc, scores.sum(axis=1).reshape(n, 1)), axis=1), 50, 100)
+    np.savez_compressed(HERE / "roi_real10_w50.npz", x=x.astype(np.int8), exp=exp, window=np.int64(50),
+                        original_idx=idx.astype(np.int64), start=rois["Start"].to_numpy(np.int64),
+                        end=rois["End"].to_numpy(np.int64), rolling_max=rois["RollingMax"].to_numpy(np.float64),
+                        rolling_mean=rois["RollingMean"].to_numpy(np.float64))
+    print("wrote roi_real10_w50", len(idx))
+    rng = np.random.default_rng(17)
+    for window in (50, 125, 7):
+        n1, n2 = 3100, 2400
+        sc = (rng.standard_normal((n1 + n2, 15)) * rng.choice([0.0, 0.2, 1.0], size=(n1 + n2, 1))).astype(np.float32)
+        loc = np.empty((n1 + n2, 3), dtype=object)
+        loc[:n1, 0] = "chr1"; loc[n1:, 0] = "chr2"
+        st = np.concatenate([np.arange(n1), np.arange(n2)]) * 200
+        loc[:, 1] = st; loc[:, 2] = st + 200
+        rois, idx = maxMean(np.concatenate((loc, sc.sum(axis=1).reshape(-1, 1)), axis=1), window, 100)
+        np.savez_compressed(HERE / ("roi_synth_w%d.npz" % window), scores=sc, starts=st.astype(np.int64),
+                            chrom_split=np.int64(n1), window=np.int64(window), original_idx=idx.astype(np.int64),
+                            start=rois["Start"].to_numpy(np.int64), end=rois["End"].to_numpy(np.int64),
+                            rolling_max=rois["RollingMax"].to_numpy(np.float64),
+                            rolling_mean=rois["RollingMean"].to_numpy(np.float64))
+        print("wrote roi_synth_w%d" % window, len(idx))
+
+
 def main():
     which = set(sys.argv[1:])
 
@@ -116,6 +153,8 @@ def main():
         paired_case("paired_synth_q0_k18", xa[:400], xb[:400], 18, (1,), seed=13, quiescent_state=-1)
     if want("s3big"):
         s3_big_case("synth_s3_c833_k18")
+    if want("roi"):
+        roi_cases()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,66 @@
+"""`epilogos` command line mirror (epilogos_b200.run): flag validation on CPU, full local pipeline on the GPU."""
+import gzip
+from pathlib import Path
+
+import numpy as np
+import pytest
+from click.testing import CliRunner
+
+from test_host_stages import write_tsv
+
+META = "zero_index\tone_index\tshort_name\tlong_name\n" + "".join("%d\t%d\tS%d\tstate %d\n" % (i, i + 1, i + 1, i + 1)
+                                                                      for i in range(18))
+
+
+def test_flag_validation_messages(tmp_path):
+    from epilogos_b200 import run
+    r = CliRunner().invoke(run.main, ["-l", "-o", str(tmp_path), "-j", "x"])
+    assert "ERROR: [-i, --input-directory] required in 'single' group mode" in r.output
+    r = CliRunner().invoke(run.main, ["-m", "paired", "-a", str(tmp_path), "-o", str(tmp_path), "-j", "x"])
+    assert "ERROR: [-b, --directory-two] required in 'paired' group mode" in r.output
+    r = CliRunner().invoke(run.main, ["-i", str(tmp_path), "-o", str(tmp_path), "-j", "x", "-n"])
+    assert "not compatible with [-n, --null-distribution]" in r.output
+    meta = tmp_path / "meta.tsv"
+    meta.write_text(META)
+    assert run.getNumStates(meta) == 18 and run.getStateNames(meta)[17] == "S18"
+    inp = tmp_path / "in"
+    inp.mkdir()
+    (inp / "f.txt").write_text("chr1\t0\t200\t1\n")
+    r = CliRunner().invoke(run.main, ["-i", str(inp), "-o", str(tmp_path / "o"), "-j", str(meta), "-s", "4"])
+    assert isinstance(r.exception, ValueError) and "Saliency Metric Invalid" in str(r.exception)
+    r = CliRunner().invoke(run.main, ["-i", str(tmp_path / "missing"), "-o", str(tmp_path / "o"), "-j", str(meta)])
+    assert isinstance(r.exception, FileNotFoundError)
+    r = CliRunner().invoke(run.main, ["-v"])
+    assert "Version:" in r.output
+
+
+@pytest.mark.gpu
+def test_local_single_pipeline_end_to_end(tmp_path, golden):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from epilogos_b200 import run, session
+    from oracle import epilogos_oracle as orc, roi_oracle
+    session.clear()
+    g = golden("real10_chr1_k18")
+    x = g["x"]
+    inp = tmp_path / "mydata"; out = tmp_path / "out"
+    inp.mkdir()
+    write_tsv(inp / "epilogos_matrix_chr1.txt.gz", x, gz=True)
+    meta = tmp_path / "meta.tsv"
+    meta.write_text(META)
+    r = CliRunner().invoke(run.main, ["-l", "-i", str(inp), "-o", str(out), "-j", str(meta), "-s", "1", "-w", "20"])
+    assert r.exit_code == 0, r.output + repr(r.exception)
+    with gzip.open(out / "scores_mydata_s1_epilogos_matrix_chr1.txt.gz", "rb") as f:
+        text = f.read()
+    ref_lines = g["s1_text"].tobytes().split(b"\n")
+    got_lines = text.split(b"\n")
+    assert len(ref_lines) == len(got_lines) and sum(a != b for a, b in zip(ref_lines, got_lines)) <= 2
+    # step 4 consumed the temp files and wrote the ROI list; compare with the oracle on the reference's scores
+    assert not list(out.glob("temp_scores_*.npz")) and not (out / "exp_freq_mydata_s1.npy").exists()
+    starts = np.arange(len(x), dtype=np.int64) * 200
+    sel = roi_oracle.max_mean(starts, starts + 200, g["s1_scores"].sum(axis=1), 20, 100)
+    states = roi_oracle.max_states(g["s1_scores"], sel["original_idx"], 20)
+    want = roi_oracle.roi_text(np.array(["chr1"] * len(x), dtype=object), sel, states, ["S%d" % i for i in range(1, 19)])
+    got = (out / "regionsOfInterest_mydata_s1.txt").read_text()
+    assert [l.split("\t")[:4] for l in got.splitlines()] == [l.split("\t")[:4] for l in want.splitlines()]

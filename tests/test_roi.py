@@ -1,0 +1,74 @@
+"""Region-of-interest selection: oracle pinned to the reference's helpers.maxMean,
+product (native epi_roi_maxmean + epilogos_b200.roi) against both."""
+import numpy as np
+import pytest
+
+from oracle import epilogos_oracle as orc
+from oracle import roi_oracle
+
+
+def real_case(golden):
+    g = golden("roi_real10_w50")
+    x = g["x"]
+    scores = orc.s1_scores(x, 18, g["exp"])
+    n = len(scores)
+    starts = np.arange(n, dtype=np.int64) * 200
+    return g, scores, starts, starts + 200, np.array(["chr1"] * n, dtype=object)
+
+
+def synth_case(golden, window):
+    g = golden("roi_synth_w%d" % window)
+    sc, st = g["scores"], g["starts"]
+    n1 = int(g["chrom_split"])
+    chrom = np.array(["chr1"] * n1 + ["chr2"] * (len(sc) - n1), dtype=object)
+    return g, sc, st, st + 200, chrom
+
+
+def check(sel, g):
+    assert np.array_equal(sel["original_idx"], g["original_idx"])          # identical regions, identical ranking
+    assert np.array_equal(sel["start"], g["start"]) and np.array_equal(sel["end"], g["end"])
+    assert sel["rolling_max"].tobytes() == g["rolling_max"].tobytes()
+    np.testing.assert_allclose(sel["rolling_mean"], g["rolling_mean"], rtol=1e-13, atol=1e-15)
+
+
+def test_oracle_real_slice_matches_reference(golden):
+    g, scores, st, en, _ = real_case(golden)
+    check(roi_oracle.max_mean(st, en, scores.sum(axis=1), 50, 100), g)
+
+
+@pytest.mark.parametrize("window", [50, 125, 7])
+def test_oracle_two_chromosomes_matches_reference(golden, window):
+    g, sc, st, en, _ = synth_case(golden, window)
+    check(roi_oracle.max_mean(st, en, sc.sum(axis=1), window, 100), g)
+
+
+def test_native_selector_matches_reference(golden):
+    from epilogos_b200 import roi
+    g, scores, st, en, _ = real_case(golden)
+    check(roi.max_mean(st, en, scores.sum(axis=1), 50, 100), g)
+    for window in (50, 125, 7):
+        g, sc, st, en, _ = synth_case(golden, window)
+        check(roi.max_mean(st, en, sc.sum(axis=1), window, 100), g)
+
+
+def test_roi_file_and_max_states(golden, tmp_path):
+    from epilogos_b200 import roi
+    g, sc, st, en, chrom = synth_case(golden, 50)
+    names = ["S%d" % i for i in range(1, 16)]
+    sel = roi_oracle.max_mean(st, en, sc.sum(axis=1), 50, 100)
+    states = roi_oracle.max_states(sc, sel["original_idx"], 50)
+    want = roi_oracle.roi_text(chrom, sel, states, names)
+    # product: temp_scores npz files per chromosome -> regionsOfInterest_<tag>.txt
+    n1 = int(g["chrom_split"])
+    for name, lo, hi in (("chr2", n1, len(sc)), ("chr1", 0, n1)):
+        loc = np.empty((hi - lo, 3), dtype=object)
+        loc[:, 0] = name; loc[:, 1] = st[lo:hi]; loc[:, 2] = en[lo:hi]
+        np.savez_compressed(tmp_path / ("temp_scores_t_%s.npz" % name), chrName=np.array([name]), scoreArr=sc[lo:hi],
+                            locationArr=loc)
+    meta = tmp_path / "meta.tsv"
+    meta.write_text("zero_index\tone_index\tshort_name\n" + "".join("%d\t%d\t%s\n" % (i, i + 1, n) for i, n in enumerate(names)))
+    exp_path = tmp_path / "exp_freq_t.npy"
+    np.save(exp_path, np.zeros(3, dtype=np.float32))
+    roi.main(tmp_path, meta, "t", exp_path, 50, False)
+    assert (tmp_path / "regionsOfInterest_t.txt").read_text() == want
+    assert not exp_path.exists() and not list(tmp_path.glob("temp_scores_*.npz"))      # roiSingle.py:40, 73-74
