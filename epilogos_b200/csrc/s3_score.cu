@@ -8,99 +8,244 @@
 // restatement (oracle s3_scores_f64) at 1e-9 and agrees with the reference's float32 result to the
 // reference's own accumulation noise.
 //
-//   epi_s3_terms   E3 (float32) -> T (float64), one thread per entry.
-//   epi_scores_s3  one thread per bin; the CTA's label rows sit in shared memory (row stride an odd number of
-//                  words, so the per-thread row walks are bank-conflict free); j is register-blocked by 4 so
-//                  each label read feeds 4 table look-ups; T is read through L1/L2 (each [i][j] block of K*K
-//                  doubles is shared by all bins of the CTA).
+// The work is C(C-1) table look-ups per bin (8.7e11 for chr1 at 833 biosamples) into a 1.8 GB table: neither
+// HBM- nor tensor-shaped.  Blocking (version 2; version 1 gathered through L1 at 1.8e11 look-ups/s):
+//   * a CTA owns BC = 256*BPT consecutive bins (BPT per thread) and walks j in blocks of JC biosamples; for a
+//     j-block it keeps JC*BPT float64 accumulators per thread in registers and runs over all i;
+//   * for every (i, j-block) the JC consecutive K*K term blocks T[i][j0..j0+JC) are ONE contiguous slab, streamed
+//     into a two-stage shared-memory ring by a producer warp with 1D bulk copies (cp.async.bulk + mbarrier), so the
+//     look-ups are LDS.64 (identical (a,c) pairs across lanes -- the common case in real data -- broadcast);
+//   * labels come from a transposed copy xT[C][bins] so a thread's BPT labels of biosample i are one coalesced load;
+//   * per-bin score rows live in shared memory and are written once: no atomics, deterministic summation order.
+// T is streamed once per CTA: L2->SM traffic = (bins / BC) * 1.8 GB.
 #include "common.cuh"
 
 namespace epi {
 
-__global__ void __launch_bounds__(256) s3_terms_kernel(const float* __restrict__ e3, long long n, double q,
-                                                       double* __restrict__ terms) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double e = (double)e3[i];
-        terms[i] = (e == 0.0) ? 0.0 : q * log2(q / e);       // klScoreND masks (scores.py:550); q > 0 always
+constexpr int S3S_THREADS = 256;          // consumer threads (+ 32 producer threads)
+
+__host__ __device__ inline long long s3_block_stride(int K) { return ((long long)K * K + 1) & ~1ll; }   // 16-byte blocks
+
+// terms in padded block layout: block (i*C + j) holds K*K doubles [a][c] (+ pad), JC_MAX zero blocks at the end
+__global__ void __launch_bounds__(256) s3_terms_kernel(const float* __restrict__ e3, int cols, int K, double q,
+                                                       double* __restrict__ terms, long long nblocks_total) {
+    const long long blk = s3_block_stride(K);
+    const long long kk = (long long)K * K;
+    const long long n = nblocks_total * blk;
+    const long long nreal = (long long)cols * cols;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / blk, r = idx - b * blk;
+        double v = 0.0;
+        if (b < nreal && r < kk) {
+            const double e = (double)e3[b * kk + r];
+            v = (e == 0.0) ? 0.0 : q * log2(q / e);          // klScoreND masks (scores.py:550); q > 0 always
+        }
+        terms[idx] = v;
     }
 }
 
-constexpr int S3S_JB = 4;
-
-template <int BINS>
-__global__ void __launch_bounds__(BINS) s3_score_kernel(const int8_t* __restrict__ x, long long bins, int cols,
-                                                        long long pitch, int K, int stride_words,
-                                                        const double* __restrict__ terms, float* __restrict__ out32,
-                                                        double* __restrict__ out64) {
-    extern __shared__ __align__(16) uint32_t xs[];              // [BINS][stride_words]
-    const int tid = threadIdx.x;
-    const long long b0 = (long long)blockIdx.x * BINS;
-    const int nb = (int)((bins - b0) < BINS ? (bins - b0) : BINS);
-    // stage the label rows (coalesced along the row); rows beyond nb and bytes beyond cols are never read
-    {
-        uint8_t* xb = reinterpret_cast<uint8_t*>(xs);
-        const int row_bytes = stride_words * 4;
-        for (int r = 0; r < nb; ++r) {
-            const int8_t* src = x + (b0 + r) * pitch;
-            for (int j = tid; j < cols; j += BINS) xb[r * row_bytes + j] = (uint8_t)src[j];
-        }
+// x[bins][pitch] -> xT[cols][bp] (bins >= `bins` filled with label 0)
+__global__ void __launch_bounds__(256) s3_transpose_kernel(const int8_t* __restrict__ x, long long bins, int cols,
+                                                           long long pitch, uint8_t* __restrict__ xt, long long bp) {
+    __shared__ uint8_t tile[64][65];
+    const long long b0 = (long long)blockIdx.x * 64;
+    const int j0 = blockIdx.y * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;                   // r: bin, c: column (coalesced along columns)
+        uint8_t v = 0;
+        if (b0 + r < bins && j0 + c < cols) v = (uint8_t)x[(b0 + r) * pitch + j0 + c];
+        tile[r][c] = v;
     }
     __syncthreads();
-    if (tid >= nb) return;
-
-    const uint32_t* row = xs + (size_t)tid * stride_words;
-    const uint8_t* rowb = reinterpret_cast<const uint8_t*>(row);
-    double sc[EPI_MAX_STATES];
-#pragma unroll
-    for (int s = 0; s < EPI_MAX_STATES; ++s) sc[s] = 0.0;
-    const long long kk = (long long)K * K;
-
-    for (int j0 = 0; j0 < cols; j0 += S3S_JB) {
-        int c[S3S_JB];
-        double acc[S3S_JB];
-        const double* tj[S3S_JB];
-#pragma unroll
-        for (int jj = 0; jj < S3S_JB; ++jj) {
-            const int j = j0 + jj < cols ? j0 + jj : cols - 1;
-            c[jj] = rowb[j];
-            acc[jj] = 0.0;
-            tj[jj] = terms + (long long)j * kk + c[jj];               // + i*cols*kk + a*K below
-        }
-        for (int i = 0; i < cols; ++i) {
-            const int a = rowb[i];
-            const long long off = (long long)i * cols * kk + (long long)a * K;
-#pragma unroll
-            for (int jj = 0; jj < S3S_JB; ++jj) {
-                const double t = __ldg(tj[jj] + off);
-                if (i != j0 + jj) acc[jj] += t;
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < S3S_JB; ++jj)
-            if (j0 + jj < cols) sc[c[jj]] += acc[jj];
-    }
-    const long long b = b0 + tid;
-    for (int s = 0; s < K; ++s) {
-        if (out32 != nullptr) out32[b * K + s] = (float)sc[s];
-        if (out64 != nullptr) out64[b * K + s] = sc[s];
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, r = i & 63;                   // coalesced along bins
+        if (j0 + c < cols && b0 + r < bp) xt[(long long)(j0 + c) * bp + b0 + r] = tile[r][c];
     }
 }
+
+template <int BPT, int JC>
+__global__ void __launch_bounds__(S3S_THREADS + 32, 1)
+s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, int cols, int K,
+                const double* __restrict__ terms, float* __restrict__ out32, double* __restrict__ out64) {
+    constexpr int BC = S3S_THREADS * BPT;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int blk = (int)s3_block_stride(K);
+    const int slab_bytes = JC * blk * 8;
+    double* sc = reinterpret_cast<double*>(smem);                                   // [BC][K]
+    uint8_t* slabs = smem + (((size_t)BC * K * 8 + 127) & ~(size_t)127);           // 2 slabs
+    uint64_t* full = reinterpret_cast<uint64_t*>(slabs + 2 * (size_t)slab_bytes);
+    uint64_t* empty = full + 2;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], S3S_THREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < BC * K; i += blockDim.x) sc[i] = 0.0;
+    __syncthreads();
+
+    const int njb = (cols + JC - 1) / JC;
+    if (warp == S3S_THREADS / 32) {
+        // ---------------- producer: stream the term slabs (i, j-block) ----------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int jb = 0; jb < njb; ++jb) {
+                for (int i = 0; i < cols; ++i) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], slab_bytes);
+                    bulk_load_1d(slabs + (size_t)s * slab_bytes, terms + ((long long)i * cols + jb * JC) * blk,
+                                 slab_bytes, &full[s]);
+                    if (++s == 2) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: BPT bins per thread ----------------
+    const long long bin0 = (long long)blockIdx.x * BC + (long long)tid * BPT;
+    const uint8_t* col = xt + bin0;                          // + i * bp
+    double* my_sc = sc + (size_t)tid * BPT * K;
+    const uint32_t slab0 = smem_u32(slabs);
+    int s = 0;
+    uint32_t ph = 0;
+
+    auto load_labels = [&](int i, uint32_t (&lab)[BPT]) {
+        if constexpr (BPT == 4) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(col + (long long)i * bp);
+            lab[0] = w & 0xff; lab[1] = (w >> 8) & 0xff; lab[2] = (w >> 16) & 0xff; lab[3] = w >> 24;
+        } else if constexpr (BPT == 2) {
+            const uint32_t w = *reinterpret_cast<const uint16_t*>(col + (long long)i * bp);
+            lab[0] = w & 0xff; lab[1] = w >> 8;
+        } else {
+#pragma unroll
+            for (int u = 0; u < BPT; ++u) lab[u] = col[(long long)i * bp + u];
+        }
+    };
+
+    for (int jb = 0; jb < njb; ++jb) {
+        const int j0 = jb * JC;
+        uint32_t off[BPT][JC];       // byte offset of (jj, c) inside a slab
+        uint32_t cst[BPT][JC];       // state of biosample j0+jj in bin u
+        double acc[BPT][JC];
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+            uint32_t lab[BPT];
+            load_labels(j0 + jj < cols ? j0 + jj : cols - 1, lab);
+#pragma unroll
+            for (int u = 0; u < BPT; ++u) {
+                cst[u][jj] = lab[u];
+                off[u][jj] = (uint32_t)(jj * blk + (int)lab[u]) * 8u;
+                acc[u][jj] = 0.0;
+            }
+        }
+        uint32_t nxt[BPT];
+        load_labels(0, nxt);
+        for (int i = 0; i < cols; ++i) {
+            uint32_t a[BPT];
+#pragma unroll
+            for (int u = 0; u < BPT; ++u) a[u] = nxt[u] * (uint32_t)(K * 8);
+            if (i + 1 < cols) load_labels(i + 1, nxt);          // prefetch the next biosample's labels
+            mbar_wait(&full[s], ph);
+            const uint32_t base = slab0 + (uint32_t)s * (uint32_t)slab_bytes;
+            const bool diag = (i >= j0) && (i < j0 + JC);
+            if (!diag) {
+#pragma unroll
+                for (int u = 0; u < BPT; ++u) {
+#pragma unroll
+                    for (int jj = 0; jj < JC; ++jj) {
+                        double t;
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
+                        acc[u][jj] += t;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < BPT; ++u) {
+#pragma unroll
+                    for (int jj = 0; jj < JC; ++jj) {
+                        if (i != j0 + jj) {                      // the pair (i, i) does not exist
+                            double t;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
+                            acc[u][jj] += t;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == 2) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        // bucket by the state of the second biosample (np.add.at index dataArr[row, J], scores.py:496)
+#pragma unroll
+        for (int jj = 0; jj < JC; ++jj) {
+            if (j0 + jj < cols) {
+#pragma unroll
+                for (int u = 0; u < BPT; ++u) my_sc[u * K + cst[u][jj]] += acc[u][jj];
+            }
+        }
+    }
+    // ---------------- write the CTA's score rows ----------------
+    asm volatile("bar.sync 1, %0;" ::"r"(S3S_THREADS) : "memory");      // consumers only (the producer warp has left)
+    const long long cta_bin0 = (long long)blockIdx.x * BC;
+    const long long nvalid = (bins - cta_bin0) < BC ? (bins - cta_bin0) : BC;
+    for (long long i = tid; i < nvalid * K; i += S3S_THREADS) {
+        const double v = sc[i];
+        if (out32 != nullptr) out32[cta_bin0 * K + i] = (float)v;
+        if (out64 != nullptr) out64[cta_bin0 * K + i] = v;
+    }
+}
+
+template <int BPT, int JC>
+static int launch_s3_score(const uint8_t* xt, int64_t bp, int64_t bins, int cols, int K, const double* terms,
+                           float* o32, double* o64, cudaStream_t st) {
+    constexpr int BC = S3S_THREADS * BPT;
+    const size_t slab = (size_t)JC * s3_block_stride(K) * 8;
+    const size_t smem = (((size_t)BC * K * 8 + 127) & ~(size_t)127) + 2 * slab + 64;
+    auto kern = s3_score_kernel<BPT, JC>;
+    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((bins + BC - 1) / BC), S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, o32, o64);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+constexpr int S3S_JC_MAX = 8;
 
 }  // namespace epi
 
 using namespace epi;
+
+extern "C" int epi_s3_terms_size(int32_t cols, int32_t K, int64_t* doubles_out) {
+    EPI_REQUIRE(cols >= 2 && K >= 1 && K <= EPI_MAX_STATES && doubles_out != nullptr, "bad S3 shape");
+    *doubles_out = ((int64_t)cols * cols + S3S_JC_MAX) * s3_block_stride(K);
+    return 0;
+}
 
 extern "C" int epi_s3_terms(const float* exp3_dev, int32_t cols, int32_t K, double* terms_dev, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (check_device()) return 3;
     EPI_REQUIRE(cols >= 2 && K >= 1 && K <= EPI_MAX_STATES, "bad S3 shape (needs at least 2 biosamples)");
     EPI_REQUIRE(exp3_dev != nullptr && terms_dev != nullptr, "null pointer argument");
-    const long long n = (long long)cols * cols * K * K;
+    EPI_REQUIRE((reinterpret_cast<uintptr_t>(terms_dev) & 15) == 0, "terms_dev must be 16-byte aligned");
+    const long long nblocks = (long long)cols * cols + S3S_JC_MAX;
+    const long long n = nblocks * s3_block_stride(K);
     const double q = 1.0 / ((double)cols * (double)(cols - 1));
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    s3_terms_kernel<<<(unsigned)blocks, 256, 0, st>>>(exp3_dev, n, q, terms_dev);
+    s3_terms_kernel<<<(unsigned)blocks, 256, 0, st>>>(exp3_dev, cols, K, q, terms_dev, nblocks);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -112,23 +257,26 @@ extern "C" int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, in
     EPI_REQUIRE(bins >= 0 && cols >= 2 && pitch >= cols && K >= 1 && K <= EPI_MAX_STATES, "bad S3 shape");
     if (bins == 0 || (out32_dev == nullptr && out64_dev == nullptr)) return 0;
     EPI_REQUIRE(x_dev != nullptr && terms_dev != nullptr, "null pointer argument");
-    int stride_words = (cols + 3) / 4;
-    if ((stride_words & 1) == 0) ++stride_words;                 // odd word stride: conflict-free row walks
-    const size_t row_bytes = (size_t)stride_words * 4;
-    if (row_bytes * 256 <= 220 * 1024) {
-        auto kern = s3_score_kernel<256>;
-        const size_t smem = row_bytes * 256;
-        EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)((bins + 255) / 256), 256, smem, st>>>(x_dev, bins, cols, pitch, K, stride_words, terms_dev,
-                                                                out32_dev, out64_dev);
-    } else {
-        EPI_REQUIRE(row_bytes * 64 <= 220 * 1024, "too many biosamples (%d) for the S3 score kernel", cols);
-        auto kern = s3_score_kernel<64>;
-        const size_t smem = row_bytes * 64;
-        EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)((bins + 63) / 64), 64, smem, st>>>(x_dev, bins, cols, pitch, K, stride_words, terms_dev,
-                                                             out32_dev, out64_dev);
-    }
-    EPI_CUDA(cudaGetLastError());
-    return 0;
+    EPI_REQUIRE((reinterpret_cast<uintptr_t>(terms_dev) & 15) == 0, "terms_dev must be 16-byte aligned");
+    // choose the blocking that fits 227 KB of shared memory: score rows BC*K*8 + two slabs JC*blk*8
+    const size_t blk8 = (size_t)s3_block_stride(K) * 8;
+    int bpt = 4, jc = 8;
+    auto fits = [&](int b, int j) { return (size_t)S3S_THREADS * b * K * 8 + 2 * (size_t)j * blk8 + 256 <= 220 * 1024; };
+    if (bins <= S3S_THREADS * 2) bpt = bins <= S3S_THREADS ? 1 : 2;              // small inputs: more CTAs
+    while (!fits(bpt, jc) && bpt > 1) bpt >>= 1;
+    while (!fits(bpt, jc) && jc > 2) jc >>= 1;
+    EPI_REQUIRE(fits(bpt, jc), "S3 score blocking does not fit shared memory for K=%d", K);
+    const int64_t bc = (int64_t)S3S_THREADS * bpt;
+    const int64_t bp = ((bins + bc - 1) / bc) * bc;
+    uint8_t* xt = nullptr;
+    EPI_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xt), (size_t)(bp * cols), st));
+    dim3 tg((unsigned)((bp + 63) / 64), (unsigned)((cols + 63) / 64));
+    s3_transpose_kernel<<<tg, 256, 0, st>>>(x_dev, bins, cols, pitch, xt, bp);
+    int rc = 0;
+#define EPI_S3S_CASE(B, J) if (bpt == B && jc == J) rc = launch_s3_score<B, J>(xt, bp, bins, cols, K, terms_dev, out32_dev, out64_dev, st); else
+    EPI_S3S_CASE(4, 8) EPI_S3S_CASE(2, 8) EPI_S3S_CASE(1, 8) EPI_S3S_CASE(4, 4) EPI_S3S_CASE(2, 4) EPI_S3S_CASE(1, 4)
+    EPI_S3S_CASE(1, 2) { set_error("no S3 score kernel for blocking %d x %d", bpt, jc); rc = 2; }
+#undef EPI_S3S_CASE
+    cudaFreeAsync(xt, st);
+    return rc;
 }

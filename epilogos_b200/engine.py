@@ -208,9 +208,18 @@ def s3_terms(exp3, cols, num_states):
     _require_cuda(exp3, torch.float32, "exp3")
     if exp3.numel() != cols * cols * num_states * num_states:
         raise ValueError("expected table has %d entries, need %d" % (exp3.numel(), cols * cols * num_states ** 2))
-    terms = torch.empty(exp3.numel(), dtype=torch.float64, device=exp3.device)
+    n = ctypes.c_int64(0)
+    _lib.call("epi_s3_terms_size", int(cols), int(num_states), ctypes.byref(n))
+    terms = torch.empty(n.value, dtype=torch.float64, device=exp3.device)
     _lib.call("epi_s3_terms", _ptr(exp3), int(cols), int(num_states), _ptr(terms), _stream())
     return terms
+
+
+def s3_terms_dense(terms, cols, num_states):
+    """View of the padded term blocks as a dense [C, C, K, K] tensor (copies)."""
+    kk = num_states * num_states
+    blk = (kk + 1) & ~1
+    return terms[: cols * cols * blk].reshape(cols * cols, blk)[:, :kk].reshape(cols, cols, num_states, num_states)
 
 
 def scores_s3(x, cols, num_states, terms, want64=False, out32=None):

@@ -99,7 +99,10 @@ int epi_s3_finalize(int32_t* tiles_dev, int32_t cols, int32_t num_states, int64_
  * terms[i][j][a][c] = q log2(q / E3[i][j][a][c]), q = 1/(C(C-1)), 0 where E3 == 0   (scores.py:479-480)
  * score[b][s] = sum over ordered pairs i != j with x[b][j] == s of terms[i][j][x[b][i]][x[b][j]] (:496-498)
  * Both evaluated in float64 (the reference uses float32 and differs from exact arithmetic by its own
- * accumulation noise); terms_dev is a caller-provided C*C*K*K float64 workspace filled by epi_s3_terms. */
+ * accumulation noise).  terms_dev is a caller-provided float64 workspace of epi_s3_terms_size() doubles filled by
+ * epi_s3_terms: block (i*C + j) holds the K*K terms [a][c] of the pair, blocks are padded to an even number of
+ * doubles (16-byte bulk copies) and followed by 8 zero blocks. */
+int epi_s3_terms_size(int32_t cols, int32_t num_states, int64_t* doubles_out);
 int epi_s3_terms(const float* exp3_dev, int32_t cols, int32_t num_states, double* terms_dev, void* stream);
 int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
                   const double* terms_dev, float* out32_dev, double* out64_dev, void* stream);
