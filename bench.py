@@ -172,18 +172,24 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML queries take driver locks that can delay kernel launches on the sampled GPU, so the loop is kept light:
+        # SM clock every `period` ms, throttle reasons and power every 5th sample.
         nv = self.nv
+        period = float(os.environ.get("EPI_BENCH_CLOCK_PERIOD_MS", "10")) * 1e-3
+        i = 0
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                if i % 5 == 0:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.004)
+            i += 1
+            time.sleep(period)
 
     def start(self):
         if self.nv is not None:
@@ -236,7 +242,7 @@ def run_ours(args):
             k1_ev.append((e0, e1))
         n1, n2 = engine.expected_tables(cnt, cols, want_s1=saliency == 1, want_s2=saliency == 2)   # K2
         n = n1 if saliency == 1 else n2
-        if world > 1:
+        if world > 1 and not os.environ.get("EPI_BENCH_SKIP_ALLREDUCE"):
             dist.all_reduce(n)                                               # the path's only exchange
         e = engine.normalize(n)                                              # K4 (2 kernels)
         if saliency == 1:
