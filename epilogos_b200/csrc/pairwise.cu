@@ -175,6 +175,64 @@ __global__ void __launch_bounds__(256) quiescent_mask_kernel(const uint16_t* __r
     }
 }
 
+// ---------------------------------------------------------------- real-data reductions of the paired ROI stage
+// roiAndVisualPairwise.readInData (roiAndVisualPairwise.py:339-354) re-reads pairwiseDelta_*.txt.gz, i.e. it sees every
+// delta after a round trip through "%.5f" text -> float64 -> float32, and computes per bin
+//      distance = sum_s d^2 * sign(sum_s d)      (float32, numpy pairwise order)
+//      maxDiff  = 1-based state with the largest |d|, ties -> the higher state.
+// round5_text() reproduces the round trip arithmetically: the exact binary value is rounded half-even to 5 decimals
+// (the residual of the scaling product is recovered with one FMA, so near-ties are decided exactly), the decimal
+// q/10^5 becomes the nearest double by one correctly rounded divide (what strtod returns), then the nearest float.
+__device__ __forceinline__ float round5_text(float x) {
+    const double d = (double)x;
+    if (!(fabs(d) < 1e9)) return x;                       // printf prints all digits; no 5-decimal rounding effect that matters
+    const double ad = fabs(d);
+    const double a = ad * 1e5;
+    const double err = fma(ad, 1e5, -a);                  // ad*1e5 == a + err exactly
+    double fl = floor(a);
+    double rem = (a - fl) + err;                          // exact fractional part (|err| << 1)
+    if (rem < 0.0) {
+        fl -= 1.0;
+        rem += 1.0;
+    } else if (rem >= 1.0) {
+        fl += 1.0;
+        rem -= 1.0;
+    }
+    double q = fl;
+    if (rem > 0.5 || (rem == 0.5 && fmod(fl, 2.0) != 0.0)) q += 1.0;     // round half to even
+    const double r = q / 1e5;
+    return (float)(signbit(d) ? -r : r);
+}
+
+__global__ void __launch_bounds__(256) pairwise_real_reduce_kernel(const float* __restrict__ delta, long long rows,
+                                                                   int K, int text_round_trip,
+                                                                   float* __restrict__ dist, int* __restrict__ max_diff) {
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        const float* p = delta + r * K;
+        auto at = [&](int i) { return text_round_trip ? round5_text(p[i]) : p[i]; };
+        const float sum = numpy_rowsum_f32(K, at);
+        const float sq = numpy_rowsum_f32(K, [&](int i) {
+            const float d = at(i);
+            return __fmul_rn(d, d);
+        });
+        const float sign = sum > 0.f ? 1.f : (sum < 0.f ? -1.f : (sum == 0.f ? 0.f : sum));
+        if (dist != nullptr) dist[r] = __fmul_rn(sq, sign);
+        if (max_diff != nullptr) {
+            int best = K - 1;
+            float bv = fabsf(at(K - 1));
+            for (int s = K - 2; s >= 0; --s) {            // argmax over the flipped row: first maximum = highest state
+                const float v = fabsf(at(s));
+                if (v > bv) {
+                    bv = v;
+                    best = s;
+                }
+            }
+            max_diff[r] = best + 1;
+        }
+    }
+}
+
 static unsigned grid_for(long long n, int threads, int per_sm) {
     long long blocks = (n + threads - 1) / threads;
     const long long cap = (long long)sm_count() * per_sm;
@@ -244,6 +302,19 @@ extern "C" int epi_quiescent_mask(const uint16_t* cnt_a_dev, const uint16_t* cnt
     EPI_REQUIRE(cnt_a_dev && cnt_b_dev && mask_out, "null pointer argument");
     quiescent_mask_kernel<<<grid_for(bins, 256, 8), 256, 0, st>>>(cnt_a_dev, cnt_b_dev, bins, K, cols_a, cols_b,
                                                                   quiescent_state, mask_out);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int epi_pairwise_real_reduce(const float* delta_dev, int64_t rows, int32_t K, int32_t text_round_trip,
+                                        float* dist_out, int32_t* max_diff_out, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(rows >= 0 && K >= 1 && K <= EPI_MAX_STATES, "bad shape");
+    if (rows == 0 || (dist_out == nullptr && max_diff_out == nullptr)) return 0;
+    EPI_REQUIRE(delta_dev != nullptr, "null pointer argument");
+    pairwise_real_reduce_kernel<<<grid_for(rows, 256, 8), 256, 0, st>>>(delta_dev, rows, K, text_round_trip, dist_out,
+                                                                        max_diff_out);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }

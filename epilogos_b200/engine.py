@@ -280,3 +280,15 @@ def quiescent_mask(cnt_a, cols_a, cnt_b, cols_b, quiescent_state):
     _lib.call("epi_quiescent_mask", _ptr(cnt_a), _ptr(cnt_b), bins, k, int(cols_a), int(cols_b), int(quiescent_state),
               _ptr(mask), _stream())
     return mask
+
+
+def pairwise_real_reduce(delta, text_round_trip=True):
+    """(signed squared distance float32 [rows], max-difference state int32 [rows]) of the real deltas as the
+    reference's paired ROI stage computes them after re-reading the 5-decimal text (roiAndVisualPairwise.py:339-354)."""
+    _require_cuda(delta, torch.float32, "delta")
+    rows, k = delta.shape
+    dist = torch.empty(rows, dtype=torch.float32, device=delta.device)
+    md = torch.empty(rows, dtype=torch.int32, device=delta.device)
+    _lib.call("epi_pairwise_real_reduce", _ptr(delta), rows, k, 1 if text_round_trip else 0, _ptr(dist), _ptr(md),
+              _stream())
+    return dist, md

@@ -134,6 +134,14 @@ int epi_pairwise_combine(const float* score_a, const float* score_b, const float
 int epi_quiescent_mask(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins, int32_t num_states,
                        int32_t cols_a, int32_t cols_b, int32_t quiescent_state, uint8_t* mask_out, void* stream);
 
+/* ---- paired ROI stage reductions (roiAndVisualPairwise.readInData, roiAndVisualPairwise.py:339-354) ---------
+ * distance[b] = sum_s d^2 * sign(sum_s d) (float32, numpy pairwise order), max_diff[b] = 1-based state with the
+ * largest |d| (ties -> higher state), where d is the delta row.  With text_round_trip != 0 every delta first goes
+ * through the "%.5f" text -> float64 -> float32 round trip that the reference applies by re-reading
+ * pairwiseDelta_*.txt.gz (emulated arithmetically, bit-exact).  Either output may be NULL. */
+int epi_pairwise_real_reduce(const float* delta_dev, int64_t rows, int32_t num_states, int32_t text_round_trip,
+                             float* dist_out, int32_t* max_diff_out, void* stream);
+
 /* ---- whole path with HOST buffers (what expected.main -> expectedCombination.main -> scores.main
  *      compute for one in-memory matrix; run.py:196,231,246) ------------------------------------
  * x_host: int8 [bins][pitch] (any pitch >= cols; pinned memory makes the copies asynchronous).

@@ -358,3 +358,22 @@ def synth_states(bins, cols, num_states, seed, kind="realistic"):
     other = rng.choice(num_states, size=(bins, cols), p=prior)
     keep = rng.random((bins, cols)) < 0.6
     return np.where(keep, dom[:, None], other).astype(np.int8)
+
+
+# ------------------------------------------------------------------------------------------------
+# paired ROI stage reductions : roiAndVisualPairwise.py:339-354
+# ------------------------------------------------------------------------------------------------
+
+def text_round_trip(delta32):
+    """What readInData sees after re-reading pairwiseDelta_*.txt.gz: "%.5f" text -> float64 -> float32."""
+    flat = np.asarray(delta32, dtype=np.float32).ravel()
+    back = np.array([float("%.5f" % float(v)) for v in flat], dtype=np.float64)
+    return back.astype(np.float32).reshape(np.shape(delta32))
+
+
+def paired_real_reductions(delta32, round_trip=True):
+    """(distanceArrReal, maxDiffArr) of roiAndVisualPairwise.py:347-354."""
+    d = text_round_trip(delta32) if round_trip else np.asarray(delta32, dtype=np.float32)
+    dist = np.sum(np.square(d), axis=1) * np.sign(np.sum(d, axis=1))
+    max_diff = np.abs(np.argmax(np.abs(np.flip(d, axis=1)), axis=1) - d.shape[1]).astype(np.int32)
+    return dist, max_diff

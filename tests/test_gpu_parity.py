@@ -168,13 +168,15 @@ def test_single_host_entry_point(eng, golden, name, sal):
 
 # -------------------------------------------------------------------------------- full-size properties
 def test_whole_genome_shape_properties(eng):
-    """BASELINE config 2 width (833 biosamples, 18 states) at 2 M bins: size-independent invariants."""
+    """BASELINE configs[1] at full size (15.5 M bins x 833 biosamples x 18 states): size-independent invariants."""
     from epilogos_b200 import synth
-    bins, cols, k = 2_000_000, 833, 18
+    bins, cols, k = 15_500_000, 833, 18
     x = synth.synth_states_device(bins, cols, k, seed=21)
     cnt = eng.bin_counts(x, cols, k)
-    c64 = cnt.to(torch.int32) & 0xFFFF
-    assert bool((c64.sum(dim=1) == cols).all())                       # every label counted exactly once
+    for lo in range(0, bins, 1 << 21):                                 # every label counted exactly once
+        c32 = cnt[lo:lo + (1 << 21)].to(torch.int32) & 0xFFFF
+        assert bool((c32.sum(dim=1) == cols).all())
+    del c32
     n1, n2 = eng.expected_tables(cnt, cols)
     hist = torch.zeros(k, dtype=torch.int64, device="cuda")
     for lo in range(0, bins, 1 << 18):
@@ -362,3 +364,48 @@ def test_paired_stage_driver_device_null(eng, golden, tmp_path):
     assert null.shape == ref.shape and null.dtype == np.float32
     qs = [0.1, 0.25, 0.5, 0.75, 0.9]
     assert np.abs(np.quantile(null, qs) - np.quantile(ref, qs)).max() < 0.35 * np.std(ref)
+
+
+def test_paired_real_reductions_with_text_round_trip(eng):
+    """f2: distance + max-difference state of the real deltas exactly as the reference's paired ROI stage sees them
+    after re-parsing the 5-decimal text (roiAndVisualPairwise.py:339-354), without writing or reading any text."""
+    rng = np.random.default_rng(8)
+    k = 18
+    d = (rng.standard_normal((20000, k)) * rng.choice([1e-4, 1e-2, 1.0, 50.0], size=(20000, 1))).astype(np.float32)
+    d[:50] = np.float32(1.0 / 64)                      # exact decimal ties: 0.015625 -> "0.01562"
+    d[50:100] = np.float32(3.0 / 64) * np.float32(-1)  # -0.046875 -> "-0.04688"
+    d[100:120] = 0
+    d[120:140, 3] = np.float32(-1e-7)                   # prints "-0.00000"
+    ref_dist, ref_md = orc.paired_real_reductions(d)
+    dist, md = eng.pairwise_real_reduce(torch.from_numpy(d).cuda(), text_round_trip=True)
+    assert dist.cpu().numpy().tobytes() == ref_dist.tobytes()
+    assert np.array_equal(md.cpu().numpy(), ref_md)
+    ref_dist, ref_md = orc.paired_real_reductions(d, round_trip=False)
+    dist, md = eng.pairwise_real_reduce(torch.from_numpy(d).cuda(), text_round_trip=False)
+    assert dist.cpu().numpy().tobytes() == ref_dist.tobytes() and np.array_equal(md.cpu().numpy(), ref_md)
+
+
+def test_s3_chr1_shape_properties(eng):
+    """BASELINE configs[2] at full size (1.25 M bins x 833 biosamples x 18 states): closed-form total, symmetry,
+    empty diagonal blocks of the tensor-core Gram table; scores of a sample against the float64 oracle."""
+    from epilogos_b200 import synth
+    bins, cols, k = 1_250_000, 833, 18
+    x = synth.synth_states_device(bins, cols, k, seed=22)
+    tiles, plan = eng.s3_expected_tiles(x, cols, k)
+    counts, exp = eng.s3_finalize(tiles, cols, k, plan["mp"], bins)
+    assert int(counts.sum()) == bins * cols * (cols - 1)                         # SURVEY 8a closed form
+    idx = torch.arange(cols, device="cuda")
+    assert not bool(counts[idx, idx].any())                                      # i == j blocks stay empty
+    for lo in range(0, cols, 64):                                                # N3[i,j,a,c] == N3[j,i,c,a]
+        blk = counts[lo:lo + 64]
+        assert torch.equal(blk, counts[:, lo:lo + 64].permute(1, 0, 3, 2))
+    # pair (0, 1): against a direct 2-D histogram of the two label columns
+    pair = torch.bincount(x[:, 0].long() * k + x[:, 1].long(), minlength=k * k).reshape(k, k)
+    assert torch.equal(counts[0, 1], pair)
+    assert abs(float(exp.double().sum()) - 1.0) < 1e-6
+    terms = eng.s3_terms(exp.reshape(-1), cols, k)
+    sub = x[:1024].contiguous()
+    s32, s64 = eng.scores_s3(sub, cols, k, terms, want64=True)
+    ref = orc.s3_scores_f64(sub[:4, :cols].cpu().numpy(), k, exp.cpu().numpy())
+    np.testing.assert_allclose(s64.cpu().numpy()[:4], ref, rtol=RTOL, atol=ATOL)
+    assert bool(torch.isfinite(s32).all())
