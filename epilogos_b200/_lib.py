@@ -35,8 +35,8 @@ PROTOTYPES = {
     "epi_scores_s3": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "epi_shuffled_counts_perm": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64,
                                          c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
-    "epi_shuffled_counts_philox": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_int32,
-                                           c_void_p, c_void_p, c_void_p]),
+    "epi_shuffled_counts_philox": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_uint64,
+                                           c_int32, c_void_p, c_void_p, c_void_p]),
     "epi_pairwise_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                      c_void_p]),
     "epi_quiescent_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,

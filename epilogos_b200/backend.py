@@ -80,8 +80,8 @@ class CudaBackend:
         return engine.shuffled_counts_perm(xa, states_a.shape[1], xb, states_b.shape[1], p.contiguous(), num_states,
                                            size_a, size_b)
 
-    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1):
-        oa, ob = engine.shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm)
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None):
+        oa, ob = engine.shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm, width=width)
         return (oa[0], ob[0]) if nperm == 1 else (oa, ob)
 
     def pairwise_combine(self, score_a, score_b, null_a, null_b):

@@ -12,8 +12,8 @@
 //
 //   epi_shuffled_counts_perm    explicit permutation indices (the reference's argsort(rand) indices): used for
 //                               bit-exact parity with a seeded reference run.
-//   epi_shuffled_counts_philox  P independent uniform shuffles per bin drawn on the device: selection sampling
-//                               over the combined counts with a counter-based Philox4x32-10 stream keyed by
+//   epi_shuffled_counts_philox  P independent uniform shuffles per bin drawn on the device: multivariate hypergeometric
+//                               draws from the combined counts with a counter-based Philox4x32-10 stream keyed by
 //                               (seed, bin, permutation) -- results do not depend on grid shape or GPU count.
 //   epi_pairwise_combine        delta and signed squared null distance from the four float32 score arrays.
 //   epi_quiescent_mask          from the group counts: cntA[q] == C1 and cntB[q] == C2.
@@ -76,12 +76,52 @@ struct Philox {
     }
 };
 
-// One thread per (bin, permutation).  Selection sampling: walking over the N labels of the combined row (grouped
-// by state, which is all a count-based score can see), each label goes to A' with probability needA/remaining, to
-// B' with probability needB/remaining, else it is left out (-g group sizes smaller than the groups).
+// Hypergeometric variate by inversion from the mode (zig-zag search): number of "successes" among n draws without
+// replacement from a population of N holding K successes.  pmf(mode) comes from a shared-memory table of log(i!);
+// the search visits O(standard deviation) values.  Used per state instead of walking every label of the row
+// (6x fewer operations than per-label selection sampling at 833 biosamples).
+__device__ __forceinline__ int hypergeometric(Philox& rng, int N, int K, int n, const double* __restrict__ lf) {
+    const int lo = max(0, n - (N - K)), hi = min(n, K);
+    if (lo >= hi) return lo;
+    int mode = (int)(((long long)(n + 1) * (K + 1)) / (N + 2));
+    mode = min(max(mode, lo), hi);
+    const double logp = (lf[K] - lf[mode] - lf[K - mode]) + (lf[N - K] - lf[n - mode] - lf[N - K - n + mode]) -
+                        (lf[N] - lf[n] - lf[N - n]);
+    const float pm = (float)exp(logp);
+    // 32 random bits -> (0, 1]
+    float u = ((float)(rng.next() >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    u -= pm;
+    if (u <= 0.f) return mode;
+    int xu = mode, xd = mode;
+    float pu = pm, pd = pm;
+    for (;;) {
+        const bool can_up = xu < hi, can_dn = xd > lo;
+        if (!can_up && !can_dn) return mode;                 // rounding left-overs (probability ~1e-7)
+        if (can_up) {
+            pu *= __fdividef((float)(K - xu) * (float)(n - xu), (float)(xu + 1) * (float)(N - K - n + xu + 1));
+            ++xu;
+            u -= pu;
+            if (u <= 0.f) return xu;
+        }
+        if (can_dn) {
+            pd *= __fdividef((float)xd * (float)(N - K - n + xd), (float)(K - xd + 1) * (float)(n - xd + 1));
+            --xd;
+            u -= pd;
+            if (u <= 0.f) return xd;
+        }
+    }
+}
+
+// One thread per (bin, permutation).  A uniform shuffle of the combined row split into A' (size_a labels) and
+// B' (size_b labels) is, for count-based scores, a multivariate hypergeometric draw: walking over the states,
+//   a'_s ~ HG(remaining labels, c_s, still needed by A'),  b'_s ~ HG(remaining - needed by A', c_s - a'_s, needed by B').
 __global__ void __launch_bounds__(256) shuffled_counts_philox_kernel(
     const uint16_t* __restrict__ cnt_a, const uint16_t* __restrict__ cnt_b, long long bins, int K, int size_a,
-    int size_b, unsigned long long seed, int nperm, uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_b) {
+    int size_b, int width, unsigned long long seed, int nperm, uint16_t* __restrict__ out_a,
+    uint16_t* __restrict__ out_b) {
+    extern __shared__ double lf[];                            // log(i!), i = 0..width
+    for (int i = threadIdx.x; i <= width; i += blockDim.x) lf[i] = lgamma((double)i + 1.0);
+    __syncthreads();
     const long long total = bins * nperm;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -94,24 +134,20 @@ __global__ void __launch_bounds__(256) shuffled_counts_philox_kernel(
         rng.ctr[2] = (uint32_t)b;
         rng.ctr[3] = (uint32_t)(b >> 32);
         rng.have = 0;
-        uint32_t remaining = 0;
-        for (int s = 0; s < K; ++s) remaining += (uint32_t)cnt_a[b * K + s] + (uint32_t)cnt_b[b * K + s];
-        uint32_t need_a = size_a, need_b = size_b;
+        int remaining = 0;
+        for (int s = 0; s < K; ++s) remaining += (int)cnt_a[b * K + s] + (int)cnt_b[b * K + s];
+        int need_a = min(size_a, remaining);
+        int need_b = min(size_b, remaining - need_a);
         for (int s = 0; s < K; ++s) {
-            const uint32_t c = (uint32_t)cnt_a[b * K + s] + (uint32_t)cnt_b[b * K + s];
-            uint32_t ga = 0, gb = 0;
-            for (uint32_t i = 0; i < c; ++i) {
-                // u uniform in [0, remaining): Lemire's multiply-shift (bias < remaining / 2^32)
-                const uint32_t u = __umulhi(rng.next(), remaining);
-                if (u < need_a) {
-                    ++ga;
-                    --need_a;
-                } else if (u < need_a + need_b) {
-                    ++gb;
-                    --need_b;
-                }
-                --remaining;
+            const int c = (int)cnt_a[b * K + s] + (int)cnt_b[b * K + s];
+            int ga = 0, gb = 0;
+            if (c > 0) {
+                ga = hypergeometric(rng, remaining, c, need_a, lf);
+                gb = hypergeometric(rng, remaining - need_a, c - ga, need_b, lf);
             }
+            remaining -= c;
+            need_a -= ga;
+            need_b -= gb;
             out_a[idx * K + s] = (uint16_t)ga;
             out_b[idx * K + s] = (uint16_t)gb;
         }
@@ -263,7 +299,8 @@ extern "C" int epi_shuffled_counts_perm(const int8_t* xa_dev, int64_t pitch_a, i
 }
 
 extern "C" int epi_shuffled_counts_philox(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins,
-                                          int32_t K, int32_t size_a, int32_t size_b, uint64_t seed, int32_t nperm,
+                                          int32_t K, int32_t width, int32_t size_a, int32_t size_b, uint64_t seed,
+                                          int32_t nperm,
                                           uint16_t* cnt_a_out, uint16_t* cnt_b_out, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (check_device()) return 3;
@@ -271,8 +308,16 @@ extern "C" int epi_shuffled_counts_philox(const uint16_t* cnt_a_dev, const uint1
     EPI_REQUIRE(size_a >= 0 && size_b >= 0, "negative group size");
     if (bins == 0) return 0;
     EPI_REQUIRE(cnt_a_dev && cnt_b_dev && cnt_a_out && cnt_b_out, "null pointer argument");
-    shuffled_counts_philox_kernel<<<grid_for(bins * nperm, 256, 16), 256, 0, st>>>(
-        cnt_a_dev, cnt_b_dev, bins, K, size_a, size_b, (unsigned long long)seed, nperm, cnt_a_out, cnt_b_out);
+    EPI_REQUIRE(width >= 1 && width <= 65535, "width=%d (combined biosamples) out of range [1, 65535]", width);
+    if (size_a + size_b > width) {
+        set_error("group sizes %d + %d exceed the %d combined biosamples", size_a, size_b, width);
+        return 2;
+    }
+    const size_t smem = (size_t)(width + 1) * 8;
+    EPI_REQUIRE(smem <= 200 * 1024, "too many combined biosamples (%d) for the shuffle kernel", width);
+    EPI_CUDA(cudaFuncSetAttribute(shuffled_counts_philox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shuffled_counts_philox_kernel<<<grid_for(bins * nperm, 256, 8), 256, smem, st>>>(
+        cnt_a_dev, cnt_b_dev, bins, K, size_a, size_b, width, (unsigned long long)seed, nperm, cnt_a_out, cnt_b_out);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }

@@ -40,7 +40,8 @@ def calculateScoresPairwise(saliency, file1Path, file2Path, numStates, outputDir
         perm = np.argsort(np.random.rand(rows, c1 + c2), axis=1)                     # helpers.py:183
         null_a, null_b = be.shuffled_counts_perm(shard.states_a, shard.states_b, perm, numStates, size_a, size_b)
     else:
-        null_a, null_b = be.shuffled_counts_device(cnt_a, cnt_b, size_a, size_b, seed + 7919 * dist.rank(), nperm)
+        null_a, null_b = be.shuffled_counts_device(cnt_a, cnt_b, size_a, size_b, seed + 7919 * dist.rank(), nperm,
+                                                   width=c1 + c2)
 
     # S1 observes over the width of the array it is given (scores.py:343); S2 normalises the shuffled halves with
     # the ORIGINAL group widths even under -g (scores.py:397-398, 418-421)

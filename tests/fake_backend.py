@@ -46,7 +46,7 @@ class OracleBackend:
         sa, sb = orc.paired_split(states_a, states_b, perm, gs)
         return self.counts(sa, num_states), self.counts(sb, num_states)
 
-    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1):
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None):
         raise NotImplementedError("the test double only replays explicit permutations")
 
     def pairwise_combine(self, score_a, score_b, null_a, null_b):

@@ -344,12 +344,17 @@ def test_device_shuffle_is_a_uniform_split(eng):
     mean = oa_n.mean(axis=0)                                    # E[a'_s] = c1 * c_s / N
     expect = c1 * comb[0] / (c1 + c2)
     assert np.abs(mean - expect).max() < 1.5                    # sd of the mean ~ 0.35 at 64 permutations
+    var = oa_n.var(axis=0)                                      # Var[a'_s] = n p (1-p) (N-n)/(N-1)
+    nn = c1 + c2
+    pp = comb[0] / nn
+    vexp = c1 * pp * (1 - pp) * (nn - c1) / (nn - 1)
+    assert np.abs(var.mean(axis=0) - vexp.mean(axis=0)).max() < 0.25 * vexp.mean(axis=0).max() + 0.05
     again, _ = eng.shuffled_counts_philox(ca, cb, c1, c2, seed=99, nperm=8)
     assert torch.equal(again, oa[:8])
     other, _ = eng.shuffled_counts_philox(ca, cb, c1, c2, seed=100, nperm=8)
     assert not torch.equal(other, oa[:8])
     # -g style sub-groups: sizes respected, leftovers unassigned
-    ga, gb = eng.shuffled_counts_philox(ca, cb, 20, 20, seed=5, nperm=4)
+    ga, gb = eng.shuffled_counts_philox(ca, cb, 20, 20, seed=5, nperm=4, width=c1 + c2)
     ga_n, gb_n = eng.counts_to_numpy(ga).astype(np.int64), eng.counts_to_numpy(gb).astype(np.int64)
     assert (ga_n.sum(-1) == 20).all() and (gb_n.sum(-1) == 20).all() and ((ga_n + gb_n) <= comb).all()
 
