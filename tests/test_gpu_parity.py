@@ -414,3 +414,17 @@ def test_s3_chr1_shape_properties(eng):
     ref = orc.s3_scores_f64(sub[:4, :cols].cpu().numpy(), k, exp.cpu().numpy())
     np.testing.assert_allclose(s64.cpu().numpy()[:4], ref, rtol=RTOL, atol=ATOL)
     assert bool(torch.isfinite(s32).all())
+
+
+def test_two_gpu_stage_drivers_match_goldens(eng):
+    """Rows sharded over 2 ranks (NCCL): same files as the single-process reference goldens (tools/mgpu_check.py)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(root / "tools" / "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "MGPU ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

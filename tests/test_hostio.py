@@ -1,0 +1,86 @@
+"""Native host I/O (epi_pack_tsv / epi_write_scores_gz / epi_tsv_shape): no GPU needed."""
+import gzip
+
+import numpy as np
+import pytest
+
+from epilogos_b200 import helpers, writer
+from epilogos_b200._lib import EpilogosB200Error
+
+
+def test_writer_matches_python_format_on_edge_values(tmp_path):
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([
+        np.float32([0.0, -0.0, 1e-7, -1e-7, 5e-6, -5e-6, 1.0 / 64, 3.0 / 64, -5.0 / 64, 0.000005, 0.000015, 0.000025,
+                    123456.789, -98765.4321, 1e9, -3e12, 1e-30, 0.5, 0.99999, 0.999995, 0.9999949]),
+        (rng.standard_normal(20000) * rng.choice([1e-6, 1e-3, 1.0, 1e3], 20000)).astype(np.float32),
+        (rng.integers(-10 ** 6, 10 ** 6, 20000) / 64.0).astype(np.float32),          # many exact decimal ties
+        (rng.integers(-10 ** 7, 10 ** 7, 20000) * 1e-5).astype(np.float32),
+    ])
+    k = 7
+    vals = vals[: (len(vals) // k) * k].reshape(-1, k)
+    n = len(vals)
+    loc = dict(chrom=np.array(["chrX"] * (n // 2) + ["chr2_random"] * (n - n // 2), dtype=object),
+               start=np.arange(n, dtype=np.int64) * 200, end=np.arange(n, dtype=np.int64) * 200 + 200)
+    path = tmp_path / "s.txt.gz"
+    writer.write_scores_text(path, vals, loc, threads=3)
+    got = gzip.open(path, "rb").read().decode().splitlines()
+    assert len(got) == n
+    for i in (list(range(40)) + list(rng.integers(0, n, 3000))):
+        want = "%s\t%d\t%d\t%s" % (loc["chrom"][i], loc["start"][i], loc["end"][i],
+                                  "\t".join("{:.5f}".format(v) for v in vals[i]))
+        assert got[i] == want, (i, got[i], want)
+    # whole-file check against Python formatting
+    ref = "".join("%s\t%d\t%d\t%s\n" % (loc["chrom"][i], loc["start"][i], loc["end"][i],
+                                       "\t".join("%.5f" % float(v) for v in vals[i])) for i in range(n))
+    assert "\n".join(got) + "\n" == ref
+
+
+def test_writer_empty(tmp_path):
+    path = tmp_path / "e.txt.gz"
+    loc = dict(chrom=np.array([], dtype=object), start=np.zeros(0, np.int64), end=np.zeros(0, np.int64))
+    writer.write_scores_text(path, np.zeros((0, 18), np.float32), loc)
+    assert gzip.open(path, "rb").read() == b""
+
+
+def test_packer_shapes_ranges_and_validation(tmp_path):
+    f = tmp_path / "m.txt"
+    rows = ["chr1\t%d\t%d\t1\t18\t7" % (i * 200, i * 200 + 200) for i in range(10)]
+    f.write_text("\n".join(rows) + "\n")
+    assert helpers.tsv_shape(f) == (10, 3) and helpers.countRows(f) == 10
+    loc, s0 = helpers.read_matrix(f, num_states=18)
+    assert s0.tolist() == [[0, 17, 6]] * 10 and s0.base.shape[1] == 16 and not s0.base[:, 3:].any()
+    _, part = helpers.read_matrix(f, rows=(3, 7), num_states=18, want_locations=False)
+    assert part.shape == (4, 3)
+    # no trailing newline: the reference counts newline characters, so the last line is not a row
+    g = tmp_path / "n.txt"
+    g.write_text("\n".join(rows))
+    assert helpers.countRows(g) == 9
+    # CRLF line ends
+    h = tmp_path / "c.txt"
+    h.write_bytes(("\r\n".join(rows) + "\r\n").encode())
+    assert helpers.read_matrix(h, num_states=18)[1].tolist() == [[0, 17, 6]] * 10
+    for bad, msg in [("chr1\t0\t200\t1\t19\t7\n", "outside 1..18"), ("chr1\t0\t200\t1\t0\t7\n", "outside 1..18"),
+                     ("chr1\t0\t200\t1\tx\t7\n", "not an integer"), ("chr1\t0\t200\t1\t2\n", "state columns"),
+                     ("chr1\t0\t200\t1\t2\t3\t4\n", "more than 3")]:
+        b = tmp_path / "bad.txt"
+        b.write_text(rows[0] + "\n" + bad)
+        with pytest.raises(EpilogosB200Error, match=msg):
+            helpers.read_matrix(b, num_states=18)
+    with pytest.raises(FileNotFoundError):
+        helpers.read_matrix(tmp_path / "missing.txt")
+    with pytest.raises(EpilogosB200Error, match="only"):
+        helpers.read_matrix(f, rows=(20, 30), num_states=18)
+
+
+def test_packer_long_lines_across_buffer_blocks(tmp_path):
+    """Rows longer than any internal block boundary handling: 40 000 rows x 700 columns, gzip."""
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 25, size=(40000, 700)).astype(np.int8)
+    f = tmp_path / "big.txt.gz"
+    with gzip.open(f, "wt", compresslevel=1) as out:
+        for r in range(len(x)):
+            out.write("chr%d\t%d\t%d\t%s\n" % (1 + r // 30000, r * 200, r * 200 + 200, "\t".join(map(str, (x[r] + 1).tolist()))))
+    loc, s0 = helpers.read_matrix(f, num_states=25)
+    assert np.array_equal(s0, x)
+    assert loc["chrom"][0] == "chr1" and loc["chrom"][-1] == "chr2" and loc["start"][-1] == 39999 * 200
