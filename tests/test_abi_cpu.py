@@ -47,3 +47,24 @@ def test_no_cpu_fallback(lib):
         _lib.call("epi_bin_counts", ctypes.c_void_p(16), 1, 1, 16, 18, ctypes.c_void_p(16), ctypes.c_void_p(0))
     msg = lib.epi_last_error().decode()
     assert "no CPU fallback" in msg or "CUDA" in msg
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: if the shared library is absent the binding raises with build instructions."""
+    from epilogos_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libepilogos_b200.so")
+    with pytest.raises(_lib.EpilogosB200Error, match="no CPU fallback"):
+        _lib.call("epi_abi_version")
+    with pytest.raises(_lib.EpilogosB200Error):
+        from epilogos_b200 import helpers
+        helpers.countRows(__file__)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under epilogos_b200/ may import it."""
+    import re
+    pkg = ROOT / "epilogos_b200"
+    for f in pkg.rglob("*.py"):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
