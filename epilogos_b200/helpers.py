@@ -85,9 +85,7 @@ def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=Fal
         table = np.array([u.decode() for u in uniq], dtype=object) if uniq else np.array([], dtype=object)
         loc = dict(chrom=table[cid] if n else np.array([], dtype=object), start=starts, end=ends,
                    chrom_id=cid, chrom_names=b"\0".join(uniq) + b"\0")
-    if holder is not None:
-        read_matrix._keep = holder
-    return loc, states0
+    return loc, states0          # states0 (a numpy view) keeps the pinned torch storage alive
 
 
 def sharedToNumpy(sharedArr, numRows, numStates):

@@ -83,6 +83,37 @@ def s3_big_case(name, bins=48, cols=833, k=18, seed=11):
     print("wrote", name)
 
 
+def real_full_case():
+    """BASELINE configs[0] substitute: the whole real chr1 matrix (1,246,253 bins x 10 biosamples, 18 states) assembled
+    from /root/reference/data/ChromHMM, run through the reference's stages with 8 worker processes.  Outputs are too big to
+    commit: keep the input (0.6 MB compressed), the tables, sha256 digests of the float32 score arrays and of the
+    scores text, and the reference's own top-100 regions of interest (helpers.maxMean on its scores)."""
+    import warnings
+    x = real_slice(0, 1246253)
+    out = {"x": x.astype(np.int8), "num_states": np.int64(18)}
+    scores1 = None
+    for s in (1, 2):
+        r = ref.run_single(x, 18, s, nproc=8)
+        out["s%d_counts" % s] = r["counts"]
+        out["s%d_exp" % s] = r["exp"]
+        out["s%d_scores_sha256" % s] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(r["scores"]).tobytes()).digest(), np.uint8)
+        out["s%d_text_sha256" % s] = text_digest(r["scores_text"])
+        out["s%d_scores_head" % s] = r["scores"][:2000]
+        if s == 1:
+            scores1 = r["scores"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos.helpers import maxMean
+    n = len(scores1)
+    loc = np.empty((n, 3), dtype=object)
+    loc[:, 0] = "chr1"; loc[:, 1] = np.arange(n) * 200; loc[:, 2] = np.arange(n) * 200 + 200
+    rois, idx = maxMean(np.concatenate((loc, scores1.sum(axis=1).reshape(n, 1)), axis=1), 50, 100)
+    out.update(roi_original_idx=idx.astype(np.int64), roi_start=rois["Start"].to_numpy(np.int64),
+               roi_end=rois["End"].to_numpy(np.int64), roi_rolling_max=rois["RollingMax"].to_numpy(np.float64))
+    np.savez_compressed(HERE / "real10_chr1_full.npz", **out)
+    print("wrote real10_chr1_full")
+
+
 def roi_cases():
     """helpers.maxMean of the reference (the ROI selector that consumes the single-mode scores) on
     (a) S1 scores of a 200 000-bin real-data slice, window 50, and (b) two short synthetic chromosomes with odd /
@@ -155,6 +186,8 @@ def main():
         s3_big_case("synth_s3_c833_k18")
     if want("roi"):
         roi_cases()
+    if want("real_full"):
+        real_full_case()
 
 
 if __name__ == "__main__":

@@ -166,6 +166,30 @@ def test_single_host_entry_point(eng, golden, name, sal):
     assert np.array_equal(scores2, scores)
 
 
+# ---------------------------------------------------------------- BASELINE configs[0] (substitute): real chr1
+def test_full_real_chr1_against_reference(eng, golden):
+    """All 1,246,253 bins of the real chr1 matrix (10 biosamples, 18 states) through the host-buffer entry point: tables
+    and exp_freq payload bit-exact against the reference run, float32 scores against the oracle (itself pinned to the
+    reference's sha256 digests in test_oracle_golden.py), and the reference's own top-100 regions of interest from the
+    GPU scores: identical regions in identical order."""
+    from epilogos_b200 import roi
+    g = golden("real10_chr1_full")
+    x, k = g["x"], int(g["num_states"])
+    scores = {}
+    for sal in (1, 2):
+        counts, exp, sc = eng.single_host(eng.pack_states(x), x.shape[1], k, sal)
+        assert np.array_equal(counts, g["s%d_counts" % sal])
+        assert exp.tobytes() == g["s%d_exp" % sal].tobytes()
+        ref = orc.s1_scores(x, k, exp) if sal == 1 else orc.s2_scores(x, k, exp)
+        assert_f32_close(sc, ref)
+        assert_f32_close(sc[:2000], g["s%d_scores_head" % sal])
+        scores[sal] = sc
+    starts = np.arange(len(x), dtype=np.int64) * 200
+    sel = roi.max_mean(starts, starts + 200, scores[1].sum(axis=1), 50, 100)
+    assert np.array_equal(sel["original_idx"], g["roi_original_idx"])
+    assert np.array_equal(sel["start"], g["roi_start"]) and np.array_equal(sel["end"], g["roi_end"])
+
+
 # -------------------------------------------------------------------------------- full-size properties
 def test_whole_genome_shape_properties(eng):
     """BASELINE configs[1] at full size (15.5 M bins x 833 biosamples x 18 states): size-independent invariants."""

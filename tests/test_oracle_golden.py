@@ -112,3 +112,27 @@ def test_synth_generator_is_seeded():
     a = orc.synth_states(64, 33, 18, seed=5)
     b = orc.synth_states(64, 33, 18, seed=5)
     assert a.dtype == np.int8 and np.array_equal(a, b) and a.min() >= 0 and a.max() < 18
+
+
+def test_full_real_chr1_matches_reference_digests(golden):
+    """BASELINE configs[0] substitute: all 1,246,253 bins of the real chr1 matrix (10 biosamples, 18 states).  The
+    reference's outputs are committed as digests (tests/golden/make_golden.py real_full_case)."""
+    from oracle import roi_oracle
+    g = golden("real10_chr1_full")
+    x, k = g["x"], int(g["num_states"])
+    n1, n2 = orc.s1_expected_counts(x, k), orc.s2_expected_counts(x, k)
+    assert np.array_equal(n1, g["s1_counts"]) and np.array_equal(n2, g["s2_counts"])
+    e1, e2 = orc.normalize_expected(n1), orc.normalize_expected(n2)
+    assert e1.tobytes() == g["s1_exp"].tobytes() and e2.tobytes() == g["s2_exp"].tobytes()
+    s1 = orc.s1_scores(x, k, e1)
+    assert hashlib.sha256(np.ascontiguousarray(s1).tobytes()).digest() == g["s1_scores_sha256"].tobytes()
+    s2 = orc.s2_scores(x, k, e2)
+    assert hashlib.sha256(np.ascontiguousarray(s2).tobytes()).digest() == g["s2_scores_sha256"].tobytes()
+    assert s2[:2000].tobytes() == g["s2_scores_head"].tobytes()
+    starts = np.arange(len(s1), dtype=np.int64) * 200
+    assert hashlib.sha256(orc.format_scores_text(s1, "chr1", starts, starts + 200)).digest() == \
+        g["s1_text_sha256"].tobytes()
+    sel = roi_oracle.max_mean(starts, starts + 200, s1.sum(axis=1), 50, 100)
+    assert np.array_equal(sel["original_idx"], g["roi_original_idx"])          # the reference's own top-100 ranking
+    assert np.array_equal(sel["start"], g["roi_start"]) and np.array_equal(sel["end"], g["roi_end"])
+    assert sel["rolling_max"].tobytes() == g["roi_rolling_max"].tobytes()
