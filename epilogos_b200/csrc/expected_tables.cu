@@ -258,6 +258,8 @@ extern "C" int epi_expected_s1s2(const uint16_t* cnt_dev, int64_t bins, int32_t 
     if (bins == 0 || (n1_dev == nullptr && n2_dev == nullptr)) return 0;
     EPI_REQUIRE(cnt_dev != nullptr, "null count pointer");
     EPI_REQUIRE((reinterpret_cast<uintptr_t>(cnt_dev) & 15) == 0, "cnt_dev must be 16-byte aligned");
+    // default: the Gram form on the tensor cores (tc_tables.cu); EPI_K2_ALU=1 selects the integer-pipe kernel (A/B timing)
+    if (getenv("EPI_K2_ALU") == nullptr) return launch_k2_tc(cnt_dev, bins, K, width, n1_dev, n2_dev, st);
     if (K <= 6) return launch_k2<1>(cnt_dev, bins, K, width, n1_dev, n2_dev, st);
     if (K <= 12) return launch_k2<2>(cnt_dev, bins, K, width, n1_dev, n2_dev, st);
     if (K <= 18) return launch_k2<3>(cnt_dev, bins, K, width, n1_dev, n2_dev, st);

@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s2_kernel(const uint16_t* __res
                                                            int width, double perms, const float* __restrict__ exp2,
                                                            const PrepFlags* __restrict__ flags, int force_direct,
                                                            float* __restrict__ out32, double* __restrict__ out64) {
+    // force_direct == 2: fallback queued behind the tensor-core kernel, runs only when the table has zero entries
+    if (force_direct == 2 && !flags->has_zero) return;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint16_t* cslab = reinterpret_cast<uint16_t*>(smem_raw);                          // K5_WARPS * 2 * 32 * K u16
     float* fslab = reinterpret_cast<float*>(smem_raw + K5_WARPS * 32 * K * 4);        // K5_WARPS * 32 * K f32
@@ -321,6 +323,14 @@ template <int KT>
 static int dispatch_s2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, float* o32,
                        double* o64, int mode, cudaStream_t st) {
     const PrepFlags* flags = nullptr;
+    if (mode == EPI_SCORE_TABLE && scores_s2_tc_eligible(width) && getenv("EPI_K5_ALU") == nullptr) {
+        // tensor-core mat-vec (tc_tables.cu); a table with zero entries makes it a no-op and un-gates the DIRECT kernel
+        uint8_t* scratch = static_cast<uint8_t*>(device_scratch(nullptr));
+        EPI_REQUIRE(scratch != nullptr, "could not allocate the per-device scratch");
+        PrepFlags* fl = reinterpret_cast<PrepFlags*>(scratch + 64 * 8 + KT_MAX * KT_MAX * 8);
+        if (int rc = scores_s2_tc(cnt, bins, K, width, perms, e, &fl->has_zero, o32, o64, st)) return rc;
+        return launch_s2<KT, true>(cnt, bins, K, width, perms, e, fl, 2, o32, o64, st);
+    }
     if (int rc = prepare_tables(e, K, K, KT, st, &flags)) return rc;
     const int direct = mode == EPI_SCORE_DIRECT;
     if (width <= LC_MAX_WIDTH) return launch_s2<KT, true>(cnt, bins, K, width, perms, e, flags, direct, o32, o64, st);

@@ -1,0 +1,600 @@
+// Tensor-core forms of the two count-table contractions of the S2 path (tcgen05.mma kind::i8, exact int32
+// accumulation in TMEM).  A uint16 count is two unsigned bytes, so the per-bin count row IS an int8 operand:
+//
+//   K2 (expected.py:146-158, s2Calc)     N2[s][t] = sum_b c_bs c_bt - [s==t] c_bs
+//        G = Bt B over the bins, B[b][2s+h] = byte h of c_bs  ->  N2[s][t] = sum_{h,h'} 256^(h+h') G[2s+h][2t+h'];
+//        a row of ones appended to the operand gives N1[s] = sum_b c_bs in the same pass.
+//   K5 (scores.py:412, 443-451, s2Score) the 18x18 mat-vec  y_t = sum_s c_s (-log2 E_st)  of the TABLE evaluation
+//        (csrc/scores.cu) with -log2 E in 56-bit fixed point split into seven base-256 digits:
+//        D[b][8t+d] = sum_s lo(c_bs) dig_d(M_st) + hi(c_bs) dig_{d-1}(M_st),   Y_bt = sum_d 256^d D[b][8t+d]
+//        is the exact integer sum_s c_bs M_st; the float64 epilogue adds the O(K) remainder of the score formula.
+//
+// Both replace ALU / fp64-pipe loops that were the limiters of K2 (IMAD) and K5 (324 DFMA per bin); what is left per
+// bin is byte shuffling for K2 and ~7 fp64 operations per state for K5.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace epi {
+
+// ================================================================================================
+// K2 on the tensor cores
+//
+// Operand tile = 128 bins x 128 bytes: row b holds the 2K count bytes of bin b (zero padded), 16-byte chunks XOR-swizzled
+// by (b mod 8).  Read as an MN-major SWIZZLE_128B operand this is a [128 byte-index] x [128 bin] matrix with the bin
+// as the contraction index, so the tile is BOTH operands of G += T T^t and needs no transposition; the very same tile
+// read K-major is the A operand of the score kernel below.  Byte column 2K of every row is 1 (the N1 column).
+// ================================================================================================
+constexpr int T2_BINS = 128;          // bins per tile
+constexpr int T2_STAGES = 6;          // count-tile ring (1D bulk copies)
+constexpr int T2_OPS = 2;             // operand buffers
+constexpr int T2_OP_BYTES = 128 * 128;
+constexpr int T2_DRAIN = 256;         // tiles between accumulator drains: 255*255*32768 < 2^31
+constexpr int T2_THREADS = 192;       // warps 0-3 build operand rows, warp 4 = copy producer, warp 5 = MMA issuer
+constexpr int T2_TMEM_COLS = 128;
+
+// SM100 shared-memory descriptor of an MN-major SWIZZLE_128B operand whose MN extent is one 128-byte atom:
+// 8 contraction rows of 128 bytes per 1024-byte atom (SBO), atoms stacked along the contraction index.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((128u >> 4) & 0x3fff) << 16;       // LBO: next 128-byte MN block (unused, one block)
+    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;      // SBO: next group of 8 contraction rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t UMMA_A_MN_MAJOR = 1u << 15, UMMA_B_MN_MAJOR = 1u << 16;
+
+// the count row of one bin (KT/2 words of uint16 pairs) -> its 128-byte operand row; `ones_word`/`ones_val` put the
+// constant 1 of the N1 column into byte 2K (K2 only)
+template <int KT>
+__device__ __forceinline__ void store_operand_row(uint8_t* row_ptr, int r, const uint32_t (&cw)[KT / 2], int ones_word,
+                                                  uint32_t ones_val) {
+    constexpr int NW = ((KT / 2 + 1 + 3) / 4) * 4;     // words incl. the ones byte, whole 16-byte chunks
+#pragma unroll
+    for (int q = 0; q < NW / 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w[i] = (4 * q + i < KT / 2) ? cw[4 * q + i] : 0u;
+            if (4 * q + i == ones_word) w[i] |= ones_val;
+        }
+        *reinterpret_cast<uint4*>(row_ptr + ((q ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void load_count_row(const uint16_t* row, int K, bool live, uint32_t (&cw)[KT / 2]) {
+#pragma unroll
+    for (int i = 0; i < KT / 2; ++i)
+        cw[i] = (live && 2 * i < K ? (uint32_t)row[2 * i] : 0u) | ((live && 2 * i + 1 < K ? (uint32_t)row[2 * i + 1] : 0u) << 16);
+}
+
+// Accumulator rows m = 2s (low-byte row of state s) and 2s+1 (high-byte row) live in adjacent lanes; lane 2s combines
+// them into N2[s][.] and N1[s] (the ones column is column 2K) and adds them to the global int64 tables.  No smem.
+template <int NCOL>
+__device__ __forceinline__ void drain_gram(uint32_t tmem_lane_base, int warp, int lane, int K, unsigned long long* n1,
+                                           unsigned long long* n2) {
+    uint32_t v[NCOL];
+#pragma unroll
+    for (int c0 = 0; c0 < NCOL; c0 += 16) {
+        uint32_t t16[16];
+        tmem_ld_32x16(tmem_lane_base + (uint32_t)c0, t16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c0 + j] = t16[j];
+    }
+    const int m = warp * 32 + lane;
+    const int s = m >> 1;
+    const bool owner = (m & 1) == 0 && s < K;
+    long long diag = 0, cnt1 = 0;
+#pragma unroll
+    for (int q = 0; q < NCOL / 2; ++q) {
+        const uint32_t p0 = __shfl_down_sync(0xffffffffu, v[2 * q], 1), p1 = __shfl_down_sync(0xffffffffu, v[2 * q + 1], 1);
+        const long long val = (long long)v[2 * q] + 256ll * (long long)v[2 * q + 1] + 256ll * ((long long)p0 + 256ll * (long long)p1);
+        if (q == K) cnt1 = val;                                   // sum_b c_bs
+        else if (q == s) diag = val;                              // sum_b c_bs^2
+        else if (owner && q < K && n2 != nullptr && val != 0) atomicAdd(&n2[s * K + q], (unsigned long long)val);
+    }
+    if (owner) {
+        diag -= cnt1;                                             // c*(c-1) on the diagonal
+        if (n2 != nullptr && diag != 0) atomicAdd(&n2[s * K + s], (unsigned long long)diag);
+        if (n1 != nullptr && cnt1 != 0) atomicAdd(&n1[s], (unsigned long long)cnt1);
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(T2_THREADS, 2)
+k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned long long* __restrict__ n1,
+             unsigned long long* __restrict__ n2) {
+    constexpr int NCOL = ((2 * KT + 1) + 15) & ~15;                 // UMMA N: count bytes + the ones column
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tile_bytes = T2_BINS * K * 2;                         // multiple of 256
+    uint8_t* ops = smem;                                            // T2_OPS x [128 bins x 128 B]
+    uint8_t* ring = ops + T2_OPS * T2_OP_BYTES;
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(ring + T2_STAGES * tile_bytes);
+    uint64_t* ld_empty = ld_full + T2_STAGES;
+    uint64_t* op_full = ld_empty + T2_STAGES;
+    uint64_t* op_empty = op_full + T2_OPS;
+    uint64_t* acc_full = op_empty + T2_OPS;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (bins + T2_BINS - 1) / T2_BINS;
+    const long long nfull = bins / T2_BINS;
+
+    for (int i = tid; i < T2_OPS * T2_OP_BYTES / 16; i += T2_THREADS)
+        reinterpret_cast<uint4*>(ops)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        for (int s = 0; s < T2_STAGES; ++s) {
+            mbar_init(&ld_full[s], 1);
+            mbar_init(&ld_empty[s], 4);
+        }
+        for (int o = 0; o < T2_OPS; ++o) {
+            mbar_init(&op_full[o], 4);
+            mbar_init(&op_empty[o], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 2);
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, T2_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------ bulk-copy producer ------------------------------
+        if (lane == 0) {
+            int i = 0;
+            for (long long t = blockIdx.x; t < nfull; t += gridDim.x, ++i) {
+                const int s = i % T2_STAGES;
+                mbar_wait_wd(&ld_empty[s], (((uint32_t)(i / T2_STAGES)) & 1u) ^ 1u);
+                mbar_expect_tx(&ld_full[s], (uint32_t)tile_bytes);
+                bulk_load_1d(ring + s * tile_bytes, cnt + t * (long long)T2_BINS * K, (uint32_t)tile_bytes, &ld_full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------ MMA issuer (one thread) ------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_i8_idesc(128, NCOL) | UMMA_A_MN_MAJOR | UMMA_B_MN_MAJOR;
+            uint32_t acc = 0, dph = 0;
+            int i = 0;
+            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+                const int o = i % T2_OPS;
+                mbar_wait_wd(&op_full[o], ((uint32_t)(i / T2_OPS)) & 1u);
+                tc_fence_after();
+                const uint64_t desc = make_mnmajor_sw128_desc(smem_u32(ops + o * T2_OP_BYTES));
+#pragma unroll
+                for (int k = 0; k < T2_BINS / 32; ++k) {
+                    // 32 bins = 4 atoms of 1024 bytes further along the contraction index
+                    umma_i8(tmem_base, desc + 256 * k, desc + 256 * k, idesc, acc);      // A and B are the same tile
+                    acc = 1;
+                }
+                umma_commit(&op_empty[o]);
+                if ((i + 1) % T2_DRAIN == 0 || t + gridDim.x >= ntiles) {
+                    umma_commit(acc_full);
+                    mbar_wait_wd(acc_empty, dph);
+                    dph ^= 1;
+                    tc_fence_after();
+                    acc = 0;
+                }
+            }
+        }
+    } else {
+        // ------------------------------ operand builders: one bin per thread ------------------------------
+        uint32_t dph = 0;
+        int i = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+            const int s = i % T2_STAGES, o = i % T2_OPS;
+            uint32_t cw[KT / 2];
+            if (t < nfull) {
+                mbar_wait_wd(&ld_full[s], ((uint32_t)(i / T2_STAGES)) & 1u);
+                load_count_row<KT>(reinterpret_cast<const uint16_t*>(ring + s * tile_bytes) + tid * K, K, true, cw);
+            } else {
+                const long long b = t * T2_BINS + tid;
+                load_count_row<KT>(cnt + b * K, K, b < bins, cw);
+            }
+            mbar_wait_wd(&op_empty[o], (((uint32_t)(i / T2_OPS)) & 1u) ^ 1u);
+            // byte 2K of the row = 1 for live bins (N1 column)
+            const bool live = t * T2_BINS + tid < bins;
+            store_operand_row<KT>(ops + o * T2_OP_BYTES + tid * 128, tid, cw, K / 2,
+                                  live ? (1u << (16 * (K & 1))) : 0u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&op_full[o]);
+                if (t < nfull) mbar_arrive(&ld_empty[s]);      // released only after the loaded counts were consumed (see K5)
+            }
+
+            if ((i + 1) % T2_DRAIN == 0 || t + gridDim.x >= ntiles) {
+                mbar_wait_wd(acc_full, dph);
+                dph ^= 1;
+                tc_fence_after();
+                if (warp < 2) {
+                    drain_gram<NCOL>(tmem_base + ((uint32_t)(warp * 32) << 16), warp, lane, K, n1, n2);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, T2_TMEM_COLS);
+}
+
+template <int KT>
+static int launch_k2_tc_impl(const uint16_t* cnt, int64_t bins, int K, int64_t* n1, int64_t* n2, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)T2_OPS * T2_OP_BYTES + (size_t)T2_STAGES * T2_BINS * K * 2 +
+                        (2 * T2_STAGES + 2 * T2_OPS + 2) * 8 + 16;
+    auto kern = k2_tc_kernel<KT>;
+    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (bins + T2_BINS - 1) / T2_BINS;
+    kern<<<persistent_grid(ntiles, 2), T2_THREADS, smem, st>>>(cnt, (long long)bins, K,
+                                                                reinterpret_cast<unsigned long long*>(n1),
+                                                                reinterpret_cast<unsigned long long*>(n2));
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_k2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n1, int64_t* n2, cudaStream_t st) {
+    (void)width;
+    if (K <= 16) return launch_k2_tc_impl<16>(cnt, bins, K, n1, n2, st);
+    if (K <= 18) return launch_k2_tc_impl<18>(cnt, bins, K, n1, n2, st);
+    return launch_k2_tc_impl<32>(cnt, bins, K, n1, n2, st);
+}
+
+// ================================================================================================
+// K5 (S2) on the tensor cores
+// ================================================================================================
+constexpr int T5_BINS = 128;
+constexpr int T5_A_BYTES = 128 * 128;
+constexpr unsigned long long T5_MAGIC = 0x4338000000000000ull;      // bits of 2^52 + 2^51: integer <-> double without I2F
+constexpr int T5_MAX_WIDTH = 2047;
+
+__device__ __forceinline__ unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct K5TcConsts {
+    unsigned long long cl[EPI_MAX_STATES];      // MAGIC - (M_tt mod 2^32)   (the [s==t] term, folded into the integer sum)
+    unsigned long long ch[EPI_MAX_STATES];      // MAGIC - (M_tt div 2^32)
+    double scale;                               // 2^-F / perms
+    double cst;                                 // (2^52 + 2^51) * scale
+    int has_zero;
+    uint32_t m1, m8, m16;                       // 1, 2^8, 2^16 (opaque to the compiler)
+};
+__constant__ K5TcConsts c_k5tc;
+
+// one CTA: float32 expected table -> fixed-point digits of -log2 E laid out as the 128-byte-swizzled B operand
+// (row n = 8t + d, byte k = 2s + h holds digit d-h of M_st), per-state constants, zero flag.
+__global__ void k5tc_prepare_kernel(const float* __restrict__ e, int K, double perms, int nrows,
+                                    uint8_t* __restrict__ b_image, K5TcConsts* __restrict__ out, int* __restrict__ zero_flag) {
+    __shared__ unsigned long long mfix[EPI_MAX_STATES * EPI_MAX_STATES];
+    __shared__ double mval[EPI_MAX_STATES * EPI_MAX_STATES];
+    __shared__ unsigned long long maxbits;
+    __shared__ int zero, fbits;
+    if (threadIdx.x == 0) {
+        maxbits = 0ull;
+        zero = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+        const double ev = (double)e[i];
+        double m = 0.0;
+        if (ev > 0.0) m = -log2(ev);
+        else zero = 1;
+        if (m < 0.0) m = 0.0;                      // E <= 1 always; guards -0.0
+        mval[i] = m;
+        atomicMax(&maxbits, (unsigned long long)__double_as_longlong(m));      // non-negative doubles order like integers
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double mx = __longlong_as_double((long long)maxbits);
+        int ib = 1;
+        while (ib < 12 && (double)(1ull << ib) <= mx) ++ib;       // mx < 2^ib
+        fbits = 56 - ib;
+    }
+    __syncthreads();
+    const int F = fbits;
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+        unsigned long long v = (unsigned long long)llrint(ldexp(mval[i], F));
+        if (v >= (1ull << 56)) v = (1ull << 56) - 1;
+        mfix[i] = v;
+    }
+    for (int i = threadIdx.x; i < nrows * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(b_image)[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K * 14; i += blockDim.x) {
+        const int dd = i % 7, h = (i / 7) & 1, st = i / 14;
+        const int s = st / K, t = st - s * K;
+        const uint32_t n = (uint32_t)(t * 8 + dd + h), k = (uint32_t)(2 * s + h);
+        b_image[sw128_offset(n, k)] = (uint8_t)((mfix[st] >> (8 * dd)) & 255ull);
+    }
+    if (threadIdx.x < K) {
+        const unsigned long long mtt = mfix[threadIdx.x * K + threadIdx.x];
+        out->cl[threadIdx.x] = T5_MAGIC - (mtt & 0xffffffffull);
+        out->ch[threadIdx.x] = T5_MAGIC - (mtt >> 32);
+    }
+    if (threadIdx.x == 0) {
+        const double scale = ldexp(1.0, -F) / perms;
+        out->scale = scale;
+        out->cst = 6755399441055744.0 * scale;          // 2^52 + 2^51
+        out->has_zero = zero;
+        out->m1 = 1u;
+        out->m8 = 1u << 8;
+        out->m16 = 1u << 16;
+        *zero_flag = zero;
+    }
+}
+
+// KT: even unroll bound on the state index; KR: the state count when known at compile time (0 = runtime K <= KT);
+// NWG: warpgroups = accumulator regions in TMEM; WANT64: also write the unrounded float64 scores (tests).
+template <int KT, int KR, int NWG, bool WANT64>
+__global__ void __launch_bounds__(NWG * 128 + 64, 1)
+k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int width, double perms,
+                const uint8_t* __restrict__ b_image, float* __restrict__ out32, double* __restrict__ out64, int dbg) {
+    if (c_k5tc.has_zero) return;          // masked terms: the DIRECT kernel launched behind this one does the work
+
+    static_assert(KT % 2 == 0, "KT must be even");
+    constexpr int NPAD = ((8 * KT + 31) / 32) * 32;          // TMEM columns per warpgroup
+    static_assert(NPAD * NWG <= 512, "accumulator regions exceed TMEM");
+    constexpr int KSTEPS = (2 * KT + 31) / 32;               // UMMA K steps (32 bytes each)
+    const int K = KR ? KR : Krt;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int slab_bytes = T5_BINS * K * 2;                                  // multiple of 256
+    uint8_t* a_ops = smem;                                                   // NWG x 16 KB
+    uint8_t* b_op = a_ops + NWG * T5_A_BYTES;                                // NPAD x 128 B
+    uint8_t* slabs = b_op + NPAD * 128;                                      // NWG x 2 x slab_bytes
+    float* stage = reinterpret_cast<float*>(slabs + NWG * 2 * slab_bytes);   // NWG x 128 x K
+    double2* fh = reinterpret_cast<double2*>(stage + NWG * T5_BINS * K);     // width + 1 entries {F, HG}
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(fh + width + 1);         // [NWG][2]
+    uint64_t* ld_empty = ld_full + NWG * 2;
+    uint64_t* a_full = ld_empty + NWG * 2;                                   // [NWG]
+    uint64_t* mma_done = a_full + NWG;                                       // [NWG]
+    uint64_t* b_full = mma_done + NWG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NT = NWG * 128 + 64;
+    const long long ntiles = (bins + T5_BINS - 1) / T5_BINS;
+    const long long nfull = bins / T5_BINS;
+
+    for (int i = tid; i < NWG * T5_A_BYTES / 16; i += NT) reinterpret_cast<uint4*>(a_ops)[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+        // F[c] = c log2(c) / P,  HG[c] = ((log2 c - log2 P)(W - 1) - c log2 c + (c-1) log2(c-1)) / P      (scores.cu header)
+        const double lp = log2(perms), invp = 1.0 / perms, wm1 = (double)width - 1.0;
+        for (int c = tid; c <= width; c += NT) {
+            const double l = c > 0 ? log2((double)c) : 0.0;
+            const double l1 = c > 1 ? log2((double)(c - 1)) : 0.0;
+            const double cl = (double)c * l;
+            double2 v;
+            v.x = cl * invp;
+            v.y = (fma(l - lp, wm1, -cl) + (double)(c > 0 ? c - 1 : 0) * l1) * invp;
+            fh[c] = v;
+        }
+    }
+    fence_proxy_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < NWG * 2; ++i) {
+            mbar_init(&ld_full[i], 1);
+            mbar_init(&ld_empty[i], 4);
+        }
+        for (int g = 0; g < NWG; ++g) {
+            mbar_init(&a_full[g], 4);
+            mbar_init(&mma_done[g], 1);
+        }
+        mbar_init(b_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4 * NWG + 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4 * NWG) {
+        // ------------------------------ bulk-copy producer ------------------------------
+        if (lane == 0) {
+            mbar_expect_tx(b_full, NPAD * 128);
+            bulk_load_1d(b_op, b_image, NPAD * 128, b_full);
+            int j = 0;
+            for (long long t = blockIdx.x; t < nfull; t += gridDim.x, ++j) {
+                const int g = j % NWG, u = j / NWG, b = u & 1;
+                mbar_wait_wd(&ld_empty[g * 2 + b], (((uint32_t)(u >> 1)) & 1u) ^ 1u);
+                mbar_expect_tx(&ld_full[g * 2 + b], (uint32_t)slab_bytes);
+                bulk_load_1d(slabs + (g * 2 + b) * slab_bytes, cnt + t * (long long)T5_BINS * K, (uint32_t)slab_bytes,
+                             &ld_full[g * 2 + b]);
+            }
+        }
+    } else if (warp == 4 * NWG + 1) {
+        // ------------------------------ MMA issuer (one thread) ------------------------------
+        if (lane == 0) {
+            const uint32_t nmma = (uint32_t)((8 * K + 15) & ~15);
+            const uint32_t idesc = umma_i8_idesc(128, nmma);
+            mbar_wait_wd(b_full, 0);
+            const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(b_op));
+            int j = 0;
+            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+                const int g = j % NWG, u = j / NWG;
+                mbar_wait_wd(&a_full[g], ((uint32_t)u) & 1u);
+                tc_fence_after();
+                const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(a_ops + g * T5_A_BYTES));
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                    umma_i8(tmem_base + (uint32_t)(g * NPAD), a_desc + 2 * k, b_desc + 2 * k, idesc, k ? 1u : 0u);
+                umma_commit(&mma_done[g]);
+            }
+        }
+    } else {
+        // ------------------------------ warpgroups: one bin per thread ------------------------------
+        const int g = warp >> 2, r = tid & 127;
+        uint8_t* a_row = a_ops + g * T5_A_BYTES + r * 128;
+        float* mystage = stage + g * T5_BINS * K;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * NPAD);
+        const double scale = c_k5tc.scale, cst = c_k5tc.cst;
+        int u = 0;
+        for (long long t = blockIdx.x + (long long)g * gridDim.x; t < ntiles; t += (long long)NWG * gridDim.x, ++u) {
+            const long long bin0 = t * T5_BINS;
+            const int b = u & 1;
+            uint32_t c[KT];
+            if (t < nfull) {
+                mbar_wait_wd(&ld_full[g * 2 + b], ((uint32_t)(u >> 1)) & 1u);
+                const uint16_t* row = reinterpret_cast<const uint16_t*>(slabs + (g * 2 + b) * slab_bytes) + r * K;
+#pragma unroll
+                for (int s = 0; s < KT; ++s) c[s] = s < K ? (uint32_t)row[s] : 0u;
+            } else {
+                const bool live = bin0 + r < bins;
+                const uint16_t* row = cnt + (bin0 + r) * K;
+#pragma unroll
+                for (int s = 0; s < KT; ++s) c[s] = (live && s < K) ? (uint32_t)row[s] : 0u;
+            }
+            {
+                uint32_t cw[KT / 2];
+#pragma unroll
+                for (int i = 0; i < KT / 2; ++i) cw[i] = c[2 * i] | (c[2 * i + 1] << 16);
+                store_operand_row<KT>(a_row, r, cw, -1, 0u);        // the count row's bytes ARE the K-major A operand row
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_full[g]);
+                // The slab is released only here, after the operand stores have CONSUMED every loaded count: an arrive
+                // issued right behind the loads can be performed before they return (measured: corrupted rows when the
+                // 30-byte row pitch of 15-state models makes the loads replay), and the producer would overwrite the slab.
+                if (t < nfull) mbar_arrive(&ld_empty[g * 2 + b]);
+            }
+
+            // work that does not need the accumulators: A = sum_s F[c_s]      (c = 0 for s >= K: F[0] = 0)
+            double a = 0.0;
+#pragma unroll
+            for (int s = 0; s < KT; ++s) a += fh[c[s]].x;
+            const double a_adj = a - cst;
+
+            if (r == 0) bulk_wait_read0();             // the previous tile's rows have left the staging buffer
+            named_barrier(1 + g, 128);
+            mbar_wait_wd(&mma_done[g], ((uint32_t)u) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < 8 * KT; c0 += 32) {
+                uint32_t v[32];
+                double hg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hg[i] = (c0 / 8 + i < KT) ? fh[c[c0 / 8 + i < KT ? c0 / 8 + i : 0]].y : 0.0;
+                tmem_ld_32x32(taddr + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int tt = c0 / 8 + i;
+                    if (tt < KT && (KR == 0 || tt < KR)) {
+                        // exact integer sum_s (c_s - [s==t]) M_st = H 2^32 + L, both halves as doubles via the magic bits
+                        // digits are < 2^22, so pairs combine in 32 bits; multipliers come from constant memory so
+                        // that they stay IMAD / IMAD.WIDE operands instead of being strength-reduced to shifts + adds
+                        const uint32_t t01 = mad_lo(v[8 * i + 1], c_k5tc.m8, v[8 * i]);
+                        const uint32_t t23 = mad_lo(v[8 * i + 3], c_k5tc.m8, v[8 * i + 2]);
+                        const uint32_t t45 = mad_lo(v[8 * i + 5], c_k5tc.m8, v[8 * i + 4]);
+                        const uint32_t t67 = mad_lo(v[8 * i + 7], c_k5tc.m8, v[8 * i + 6]);
+                        const unsigned long long lb = mad_wide(t23, c_k5tc.m16, c_k5tc.cl[tt]) + (unsigned long long)t01;
+                        const unsigned long long hb = mad_wide(t67, c_k5tc.m16, c_k5tc.ch[tt]) + (unsigned long long)t45;
+                        const double dl = __longlong_as_double((long long)lb);                           // L + magic
+                        const double dh = __longlong_as_double((long long)hb) - 6755399441055744.0;    // H
+                        const double yd = fma(dh, 4294967296.0, dl);
+                        const double br = fma(yd, scale, a_adj) + hg[i];
+                        const double cd = __hiloint2double(0x43300000, (int)c[tt]) - 4503599627370496.0;
+                        const double val = fma(cd, br, 0.0);      // absent state: (+-0) + (+0) = +0.0 as in the reference
+                        if (KR != 0 || tt < K) {
+                            mystage[r * K + tt] = (float)val;
+                            if (WANT64 && bin0 + r < bins) out64[(bin0 + r) * K + tt] = val;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            named_barrier(1 + g, 128);
+            if (out32 != nullptr) {
+                if (t < nfull) {
+                    if (r == 0) {
+                        bulk_store_1d(out32 + bin0 * K, mystage, (uint32_t)(T5_BINS * K * 4));
+                        bulk_commit();
+                    }
+                } else {
+                    const int n = (int)(bins - bin0) * K;
+                    for (int i = r; i < n; i += 128) out32[bin0 * K + i] = mystage[i];
+                }
+            }
+        }
+        if (r == 0) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4 * NWG + 1) tmem_dealloc(tmem_base, 512);
+}
+
+static uint8_t* k5tc_workspace() {
+    static uint8_t* base[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (base[dev] == nullptr && cudaMalloc(reinterpret_cast<void**>(&base[dev]), 256 * 128 + 1024) != cudaSuccess) return nullptr;
+    return base[dev];
+}
+
+template <int KT, int KR, int NWG, bool WANT64>
+static int launch_k5_tc2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const uint8_t* ws, float* o32,
+                         double* o64, cudaStream_t st) {
+    constexpr int NPAD = ((8 * KT + 31) / 32) * 32;
+    auto kern = k5_s2_tc_kernel<KT, KR, NWG, WANT64>;
+    const size_t smem = 1024 + (size_t)NWG * T5_A_BYTES + (size_t)NPAD * 128 + (size_t)NWG * 2 * T5_BINS * K * 2 +
+                        (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 1) * 16 + (size_t)(6 * NWG + 1) * 8 + 16;
+    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (bins + T5_BINS - 1) / T5_BINS;
+    kern<<<persistent_grid(ntiles, 1), NWG * 128 + 64, smem, st>>>(cnt, (long long)bins, K, width, (double)perms, ws, o32, o64,
+                                                                    getenv("EPI_K5_DBG") ? atoi(getenv("EPI_K5_DBG")) : 0);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int KT, int KR, int NWG>
+static int launch_k5_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
+                        float* o32, double* o64, cudaStream_t st) {
+    constexpr int NPAD = ((8 * KT + 31) / 32) * 32;
+    uint8_t* ws = k5tc_workspace();
+    EPI_REQUIRE(ws != nullptr, "could not allocate the score-table workspace");
+    K5TcConsts* consts = reinterpret_cast<K5TcConsts*>(ws + 256 * 128);
+    k5tc_prepare_kernel<<<1, 256, 0, st>>>(e, K, (double)perms, NPAD, ws, consts, zero_flag);
+    EPI_CUDA(cudaGetLastError());
+    EPI_CUDA(cudaMemcpyToSymbolAsync(c_k5tc, consts, sizeof(K5TcConsts), 0, cudaMemcpyDeviceToDevice, st));
+    if (o64 != nullptr) return launch_k5_tc2<KT, KR, NWG, true>(cnt, bins, K, width, perms, ws, o32, o64, st);
+    return launch_k5_tc2<KT, KR, NWG, false>(cnt, bins, K, width, perms, ws, o32, o64, st);
+}
+
+// TABLE evaluation of the S2 scores on the tensor cores.  Writes *zero_flag (device int) = 1 and does nothing else when
+// the expected table has a zero entry; the caller queues the DIRECT kernel behind it, gated on that flag.
+int scores_s2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
+                 float* o32, double* o64, cudaStream_t st) {
+    if (K == 18) return launch_k5_tc<18, 18, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+    if (K == 15 && getenv("EPI_K5_NWG3")) return launch_k5_tc<16, 15, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+    if (K == 15) return launch_k5_tc<16, 15, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+    if (K <= 16) return launch_k5_tc<16, 0, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+    if (K <= 18) return launch_k5_tc<18, 0, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+    return launch_k5_tc<32, 0, 2>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
+}
+
+bool scores_s2_tc_eligible(int width) { return width <= T5_MAX_WIDTH; }
+
+}  // namespace epi
