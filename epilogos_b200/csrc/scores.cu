@@ -114,33 +114,47 @@ __device__ __forceinline__ void warp_store_scores(const float* slab, float* __re
 }
 
 // ---- S1 -----------------------------------------------------------------------------------------
-template <bool USE_LC>
+// A bin's S1 score for state s depends only on (s, c_s), and c_s <= width: all K x (width+1) possible values are
+// evaluated ONCE with the reference's own formula (float64 divide, divide, log2, multiply -- scores.py:339-344, 550)
+// and the per-bin work is a table look-up.  The float32 output is therefore the float32 rounding of exactly the
+// float64 expression the reference evaluates (no re-association: rankings downstream, e.g. the regions of interest,
+// see the same values), and the kernel is bound by its 6K bytes per bin of traffic.
+constexpr int S1_TABLE_MAX_WIDTH = 4095;
+constexpr int S1_SMEM_TABLE_BYTES = 96 * 1024;
+
+__global__ void k5_s1_table_kernel(const float* __restrict__ exp1, int K, int width, float* __restrict__ v32,
+                                   double* __restrict__ v64) {
+    const int n = K * (width + 1);
+    const double dw = (double)width;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = i / (width + 1), c = i - s * (width + 1);
+        const double v = kl_direct((double)c / dw, (double)exp1[s]);
+        v32[i] = (float)v;
+        v64[i] = v;
+    }
+}
+
+template <bool SMEM_TABLE>
 __global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
-                                                           int width, const float* __restrict__ exp1,
-                                                           const PrepFlags* __restrict__ flags, int force_direct,
+                                                           int width, const float* __restrict__ v32g,
+                                                           const double* __restrict__ v64g,
                                                            float* __restrict__ out32, double* __restrict__ out64) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint16_t* cslab = reinterpret_cast<uint16_t*>(smem_raw);                          // K5_WARPS * 2 * 32 * K u16
     float* fslab = reinterpret_cast<float*>(smem_raw + K5_WARPS * 32 * K * 4);        // K5_WARPS * 32 * K f32
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K5_WARPS * 32 * K * 8);   // K5_WARPS * 2
-    double* lc = reinterpret_cast<double*>(bars + K5_WARPS * 2);                      // width + 1
-    double* ot = lc + (USE_LC ? width + 1 : 0);                                       // width + 1
+    float* vts = reinterpret_cast<float*>(bars + K5_WARPS * 2);                       // K * (width + 1) f32
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double dw = (double)width;
-    const double lw = log2(dw);
+    const int w1 = width + 1;
     if (tid == 0) {
         for (int i = 0; i < K5_WARPS * 2; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
-    if (USE_LC) {
-        for (int i = tid; i <= width; i += K5_THREADS) {
-            lc[i] = i > 0 ? log2((double)i) : 0.0;
-            ot[i] = (double)i / dw;
-        }
-    }
+    if (SMEM_TABLE)
+        for (int i = tid; i < K * w1; i += K5_THREADS) vts[i] = v32g[i];
     __syncthreads();
-    const bool direct = force_direct || flags->has_zero;
+    const float* vt = SMEM_TABLE ? vts : v32g;
     float* myf = fslab + warp * 32 * K;
 
     const long long ngroups = (bins + 31) / 32;
@@ -155,20 +169,26 @@ __global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __res
             const uint16_t* row = myc + lane * K;
             for (int s = 0; s < K; ++s) {
                 const int c = row[s];
-                double v;
-                if (direct) {
-                    v = kl_direct((double)c / dw, (double)__ldg(exp1 + s));
-                } else if (USE_LC) {
-                    v = c > 0 ? ot[c] * (lc[c] - lw - c_log2e[s]) : 0.0;      // absent state: +0.0 as in the reference
-                } else {
-                    v = c > 0 ? ((double)c / dw) * (log2((double)c) - lw - c_log2e[s]) : 0.0;
-                }
-                myf[lane * K + s] = (float)v;
-                if (out64 != nullptr) out64[(bin0 + lane) * K + s] = v;
+                myf[lane * K + s] = vt[s * w1 + c];
+                if (out64 != nullptr) out64[(bin0 + lane) * K + s] = v64g[s * w1 + c];
             }
         }
         if (out32 != nullptr) warp_store_scores(myf, out32 + bin0 * K, nvalid, K, lane);
         else __syncwarp();
+    }
+}
+
+// per-bin evaluation (widths beyond the table limit, and the explicit DIRECT mode)
+__global__ void __launch_bounds__(K5_THREADS) k5_s1_direct_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
+                                                                  int width, const float* __restrict__ exp1,
+                                                                  float* __restrict__ out32, double* __restrict__ out64) {
+    const double dw = (double)width;
+    const long long n = bins * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i % K);
+        const double v = kl_direct((double)cnt[i] / dw, (double)__ldg(exp1 + s));
+        if (out32 != nullptr) out32[i] = (float)v;
+        if (out64 != nullptr) out64[i] = v;
     }
 }
 
@@ -294,14 +314,42 @@ static int prepare_tables(const float* e, int rows, int cols, int kt, cudaStream
     return 0;
 }
 
-template <bool USE_LC>
-static int launch_s1(const uint16_t* cnt, int64_t bins, int K, int width, const float* e, const PrepFlags* flags,
-                     int direct, float* o32, double* o64, cudaStream_t st) {
-    auto kern = k5_s1_kernel<USE_LC>;
-    const size_t smem = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16 + (USE_LC ? 2 * (size_t)(width + 1) * 8 : 0);
-    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int launch_s1(const uint16_t* cnt, int64_t bins, int K, int width, const float* e, int direct, float* o32,
+                     double* o64, cudaStream_t st) {
+    if (direct || width > S1_TABLE_MAX_WIDTH) {
+        int64_t blocks = (bins * K + K5_THREADS - 1) / K5_THREADS;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        k5_s1_direct_kernel<<<(unsigned)blocks, K5_THREADS, 0, st>>>(cnt, bins, K, width, e, o32, o64);
+        EPI_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // value table: K x (width+1) float32 + float64, in a per-device workspace
+    static uint8_t* ws[64] = {nullptr};
+    int dev = 0;
+    EPI_CUDA(cudaGetDevice(&dev));
+    EPI_REQUIRE(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    constexpr size_t kEntries = (size_t)EPI_MAX_STATES * (S1_TABLE_MAX_WIDTH + 1);
+    if (ws[dev] == nullptr) EPI_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws[dev]), kEntries * 12));
+    double* v64 = reinterpret_cast<double*>(ws[dev]);
+    float* v32 = reinterpret_cast<float*>(ws[dev] + kEntries * 8);
+    const int n = K * (width + 1);
+    k5_s1_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(e, K, width, v32, v64);
+    EPI_CUDA(cudaGetLastError());
+    const size_t base = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16;
+    const size_t table = (size_t)n * 4;
     const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
-    kern<<<persistent_grid(ntiles, k5_ctas_per_sm(4)), K5_THREADS, smem, st>>>(cnt, bins, K, width, e, flags, direct, o32, o64);
+    if (table <= (size_t)S1_SMEM_TABLE_BYTES) {
+        auto kern = k5_s1_kernel<true>;
+        EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + table)));
+        const int per_sm = (int)((size_t)220 * 1024 / (base + table + 1024));
+        kern<<<persistent_grid(ntiles, k5_ctas_per_sm(per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm))), K5_THREADS, base + table, st>>>(
+            cnt, bins, K, width, v32, v64, o32, o64);
+    } else {
+        auto kern = k5_s1_kernel<false>;
+        EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+        kern<<<persistent_grid(ntiles, k5_ctas_per_sm(4)), K5_THREADS, base, st>>>(cnt, bins, K, width, v32, v64, o32, o64);
+    }
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -360,11 +408,7 @@ extern "C" int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t K, i
     if (bins == 0 || (out32_dev == nullptr && out64_dev == nullptr)) return 0;
     EPI_REQUIRE(out32_dev == nullptr || (reinterpret_cast<uintptr_t>(out32_dev) & 15) == 0,
                 "out32_dev must be 16-byte aligned");
-    const PrepFlags* flags = nullptr;
-    if (int rc = prepare_tables(exp1_dev, 1, K, K, st, &flags)) return rc;
-    const int direct = mode == EPI_SCORE_DIRECT;
-    if (width <= LC_MAX_WIDTH) return launch_s1<true>(cnt_dev, bins, K, width, exp1_dev, flags, direct, out32_dev, out64_dev, st);
-    return launch_s1<false>(cnt_dev, bins, K, width, exp1_dev, flags, direct, out32_dev, out64_dev, st);
+    return launch_s1(cnt_dev, bins, K, width, exp1_dev, mode == EPI_SCORE_DIRECT, out32_dev, out64_dev, st);
 }
 
 extern "C" int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t K, int32_t width, int64_t perms,

@@ -36,11 +36,30 @@ __device__ __forceinline__ void named_barrier(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// mbarrier wait with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU
+// mbarrier wait: try_wait with a suspend-time hint so that a waiting warp sleeps in hardware instead of burning issue
+// slots in a polling loop, plus a watchdog: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 200000u)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+// latency-critical waits (the single MMA-issuing thread): plain polling, no suspend
+__device__ __forceinline__ void mbar_wait_spin_wd(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 28)) __trap();
     }
 }
 

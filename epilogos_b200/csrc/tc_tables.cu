@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "tc05.cuh"
+#include "count_tile.cuh"
 
 namespace epi {
 
@@ -29,85 +30,14 @@ namespace epi {
 constexpr int T2_BINS = 128;          // bins per tile
 constexpr int T2_STAGES = 6;          // count-tile ring (1D bulk copies)
 constexpr int T2_OPS = 2;             // operand buffers
-constexpr int T2_OP_BYTES = 128 * 128;
-constexpr int T2_DRAIN = 256;         // tiles between accumulator drains: 255*255*32768 < 2^31
 constexpr int T2_THREADS = 192;       // warps 0-3 build operand rows, warp 4 = copy producer, warp 5 = MMA issuer
 constexpr int T2_TMEM_COLS = 128;
 
-// SM100 shared-memory descriptor of an MN-major SWIZZLE_128B operand whose MN extent is one 128-byte atom:
-// 8 contraction rows of 128 bytes per 1024-byte atom (SBO), atoms stacked along the contraction index.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-    d |= (uint64_t)((128u >> 4) & 0x3fff) << 16;       // LBO: next 128-byte MN block (unused, one block)
-    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;      // SBO: next group of 8 contraction rows
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-constexpr uint32_t UMMA_A_MN_MAJOR = 1u << 15, UMMA_B_MN_MAJOR = 1u << 16;
-
-// the count row of one bin (KT/2 words of uint16 pairs) -> its 128-byte operand row; `ones_word`/`ones_val` put the
-// constant 1 of the N1 column into byte 2K (K2 only)
-template <int KT>
-__device__ __forceinline__ void store_operand_row(uint8_t* row_ptr, int r, const uint32_t (&cw)[KT / 2], int ones_word,
-                                                  uint32_t ones_val) {
-    constexpr int NW = ((KT / 2 + 1 + 3) / 4) * 4;     // words incl. the ones byte, whole 16-byte chunks
-#pragma unroll
-    for (int q = 0; q < NW / 4; ++q) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            w[i] = (4 * q + i < KT / 2) ? cw[4 * q + i] : 0u;
-            if (4 * q + i == ones_word) w[i] |= ones_val;
-        }
-        *reinterpret_cast<uint4*>(row_ptr + ((q ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
-template <int KT>
-__device__ __forceinline__ void load_count_row(const uint16_t* row, int K, bool live, uint32_t (&cw)[KT / 2]) {
-#pragma unroll
-    for (int i = 0; i < KT / 2; ++i)
-        cw[i] = (live && 2 * i < K ? (uint32_t)row[2 * i] : 0u) | ((live && 2 * i + 1 < K ? (uint32_t)row[2 * i + 1] : 0u) << 16);
-}
-
-// Accumulator rows m = 2s (low-byte row of state s) and 2s+1 (high-byte row) live in adjacent lanes; lane 2s combines
-// them into N2[s][.] and N1[s] (the ones column is column 2K) and adds them to the global int64 tables.  No smem.
-template <int NCOL>
-__device__ __forceinline__ void drain_gram(uint32_t tmem_lane_base, int warp, int lane, int K, unsigned long long* n1,
-                                           unsigned long long* n2) {
-    uint32_t v[NCOL];
-#pragma unroll
-    for (int c0 = 0; c0 < NCOL; c0 += 16) {
-        uint32_t t16[16];
-        tmem_ld_32x16(tmem_lane_base + (uint32_t)c0, t16);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[c0 + j] = t16[j];
-    }
-    const int m = warp * 32 + lane;
-    const int s = m >> 1;
-    const bool owner = (m & 1) == 0 && s < K;
-    long long diag = 0, cnt1 = 0;
-#pragma unroll
-    for (int q = 0; q < NCOL / 2; ++q) {
-        const uint32_t p0 = __shfl_down_sync(0xffffffffu, v[2 * q], 1), p1 = __shfl_down_sync(0xffffffffu, v[2 * q + 1], 1);
-        const long long val = (long long)v[2 * q] + 256ll * (long long)v[2 * q + 1] + 256ll * ((long long)p0 + 256ll * (long long)p1);
-        if (q == K) cnt1 = val;                                   // sum_b c_bs
-        else if (q == s) diag = val;                              // sum_b c_bs^2
-        else if (owner && q < K && n2 != nullptr && val != 0) atomicAdd(&n2[s * K + q], (unsigned long long)val);
-    }
-    if (owner) {
-        diag -= cnt1;                                             // c*(c-1) on the diagonal
-        if (n2 != nullptr && diag != 0) atomicAdd(&n2[s * K + s], (unsigned long long)diag);
-        if (n1 != nullptr && cnt1 != 0) atomicAdd(&n1[s], (unsigned long long)cnt1);
-    }
-}
-
-template <int KT>
-__global__ void __launch_bounds__(T2_THREADS, 2)
-k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned long long* __restrict__ n1,
+template <int KT, int KR>
+__global__ void __launch_bounds__(T2_THREADS, 3)
+k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, unsigned long long* __restrict__ n1,
              unsigned long long* __restrict__ n2) {
+    const int K = KR ? KR : Krt;
     constexpr int NCOL = ((2 * KT + 1) + 15) & ~15;                 // UMMA N: count bytes + the ones column
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -167,7 +97,7 @@ k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned l
             int i = 0;
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
                 const int o = i % T2_OPS;
-                mbar_wait_wd(&op_full[o], ((uint32_t)(i / T2_OPS)) & 1u);
+                mbar_wait_spin_wd(&op_full[o], ((uint32_t)(i / T2_OPS)) & 1u);
                 tc_fence_after();
                 const uint64_t desc = make_mnmajor_sw128_desc(smem_u32(ops + o * T2_OP_BYTES));
 #pragma unroll
@@ -179,7 +109,7 @@ k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned l
                 umma_commit(&op_empty[o]);
                 if ((i + 1) % T2_DRAIN == 0 || t + gridDim.x >= ntiles) {
                     umma_commit(acc_full);
-                    mbar_wait_wd(acc_empty, dph);
+                    mbar_wait_spin_wd(acc_empty, dph);
                     dph ^= 1;
                     tc_fence_after();
                     acc = 0;
@@ -195,10 +125,10 @@ k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned l
             uint32_t cw[KT / 2];
             if (t < nfull) {
                 mbar_wait_wd(&ld_full[s], ((uint32_t)(i / T2_STAGES)) & 1u);
-                load_count_row<KT>(reinterpret_cast<const uint16_t*>(ring + s * tile_bytes) + tid * K, K, true, cw);
+                load_count_row<KT, KR>(reinterpret_cast<const uint16_t*>(ring + s * tile_bytes) + tid * K, K, cw);
             } else {
                 const long long b = t * T2_BINS + tid;
-                load_count_row<KT>(cnt + b * K, K, b < bins, cw);
+                load_count_row_guarded<KT>(cnt + b * K, K, b < bins, cw);
             }
             mbar_wait_wd(&op_empty[o], (((uint32_t)(i / T2_OPS)) & 1u) ^ 1u);
             // byte 2K of the row = 1 for live bins (N1 column)
@@ -230,14 +160,16 @@ k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int K, unsigned l
     if (warp == 5) tmem_dealloc(tmem_base, T2_TMEM_COLS);
 }
 
-template <int KT>
+template <int KT, int KR>
 static int launch_k2_tc_impl(const uint16_t* cnt, int64_t bins, int K, int64_t* n1, int64_t* n2, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)T2_OPS * T2_OP_BYTES + (size_t)T2_STAGES * T2_BINS * K * 2 +
                         (2 * T2_STAGES + 2 * T2_OPS + 2) * 8 + 16;
-    auto kern = k2_tc_kernel<KT>;
+    auto kern = k2_tc_kernel<KT, KR>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + T2_BINS - 1) / T2_BINS;
-    kern<<<persistent_grid(ntiles, 2), T2_THREADS, smem, st>>>(cnt, (long long)bins, K,
+    int ctas = 3;          // measured at 15.5 M bins x 18 states: 0.33 / 0.22 / 0.19 ms with 1 / 2 / 3 CTAs per SM
+    if (const char* e = getenv("EPI_K2TC_CTAS")) ctas = atoi(e) > 0 ? atoi(e) : ctas;      // tuning knob
+    kern<<<persistent_grid(ntiles, ctas), T2_THREADS, smem, st>>>(cnt, (long long)bins, K,
                                                                 reinterpret_cast<unsigned long long*>(n1),
                                                                 reinterpret_cast<unsigned long long*>(n2));
     EPI_CUDA(cudaGetLastError());
@@ -246,9 +178,11 @@ static int launch_k2_tc_impl(const uint16_t* cnt, int64_t bins, int K, int64_t* 
 
 int launch_k2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n1, int64_t* n2, cudaStream_t st) {
     (void)width;
-    if (K <= 16) return launch_k2_tc_impl<16>(cnt, bins, K, n1, n2, st);
-    if (K <= 18) return launch_k2_tc_impl<18>(cnt, bins, K, n1, n2, st);
-    return launch_k2_tc_impl<32>(cnt, bins, K, n1, n2, st);
+    if (K == 18) return launch_k2_tc_impl<18, 18>(cnt, bins, K, n1, n2, st);
+    if (K == 15) return launch_k2_tc_impl<16, 15>(cnt, bins, K, n1, n2, st);
+    if (K <= 16) return launch_k2_tc_impl<16, 0>(cnt, bins, K, n1, n2, st);
+    if (K <= 18) return launch_k2_tc_impl<18, 0>(cnt, bins, K, n1, n2, st);
+    return launch_k2_tc_impl<32, 0>(cnt, bins, K, n1, n2, st);
 }
 
 // ================================================================================================
@@ -347,7 +281,7 @@ __global__ void k5tc_prepare_kernel(const float* __restrict__ e, int K, double p
 template <int KT, int KR, int NWG, bool WANT64>
 __global__ void __launch_bounds__(NWG * 128 + 64, 1)
 k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int width, double perms,
-                const uint8_t* __restrict__ b_image, float* __restrict__ out32, double* __restrict__ out64, int dbg) {
+                const uint8_t* __restrict__ b_image, float* __restrict__ out32, double* __restrict__ out64) {
     if (c_k5tc.has_zero) return;          // masked terms: the DIRECT kernel launched behind this one does the work
 
     static_assert(KT % 2 == 0, "KT must be even");
@@ -363,8 +297,9 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
     uint8_t* b_op = a_ops + NWG * T5_A_BYTES;                                // NPAD x 128 B
     uint8_t* slabs = b_op + NPAD * 128;                                      // NWG x 2 x slab_bytes
     float* stage = reinterpret_cast<float*>(slabs + NWG * 2 * slab_bytes);   // NWG x 128 x K
-    double2* fh = reinterpret_cast<double2*>(stage + NWG * T5_BINS * K);     // width + 1 entries {F, HG}
-    uint64_t* ld_full = reinterpret_cast<uint64_t*>(fh + width + 1);         // [NWG][2]
+    double2* t2 = reinterpret_cast<double2*>(stage + NWG * T5_BINS * K);     // width + 1 entries {c HG[c], (double)c}
+    double* f1 = reinterpret_cast<double*>(t2 + width + 1);                  // width + 1 entries F[c] (+1 pad)
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(f1 + ((width + 2) & ~1)); // [NWG][2]
     uint64_t* ld_empty = ld_full + NWG * 2;
     uint64_t* a_full = ld_empty + NWG * 2;                                   // [NWG]
     uint64_t* mma_done = a_full + NWG;                                       // [NWG]
@@ -379,15 +314,17 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
     for (int i = tid; i < NWG * T5_A_BYTES / 16; i += NT) reinterpret_cast<uint4*>(a_ops)[i] = make_uint4(0u, 0u, 0u, 0u);
     {
         // F[c] = c log2(c) / P,  HG[c] = ((log2 c - log2 P)(W - 1) - c log2 c + (c-1) log2(c-1)) / P      (scores.cu header)
+        // score_t = c_t (base_t + HG[c_t]) = fma(c_t, base_t, c_t HG[c_t]): the table holds c HG[c] and c as a double
         const double lp = log2(perms), invp = 1.0 / perms, wm1 = (double)width - 1.0;
         for (int c = tid; c <= width; c += NT) {
             const double l = c > 0 ? log2((double)c) : 0.0;
             const double l1 = c > 1 ? log2((double)(c - 1)) : 0.0;
             const double cl = (double)c * l;
+            f1[c] = cl * invp;
             double2 v;
-            v.x = cl * invp;
-            v.y = (fma(l - lp, wm1, -cl) + (double)(c > 0 ? c - 1 : 0) * l1) * invp;
-            fh[c] = v;
+            v.x = (double)c * ((fma(l - lp, wm1, -cl) + (double)(c > 0 ? c - 1 : 0) * l1) * invp);
+            v.y = (double)c;
+            t2[c] = v;
         }
     }
     fence_proxy_async_smem();
@@ -433,7 +370,7 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
             int j = 0;
             for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
                 const int g = j % NWG, u = j / NWG;
-                mbar_wait_wd(&a_full[g], ((uint32_t)u) & 1u);
+                mbar_wait_spin_wd(&a_full[g], ((uint32_t)u) & 1u);
                 tc_fence_after();
                 const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(a_ops + g * T5_A_BYTES));
 #pragma unroll
@@ -453,24 +390,14 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
         for (long long t = blockIdx.x + (long long)g * gridDim.x; t < ntiles; t += (long long)NWG * gridDim.x, ++u) {
             const long long bin0 = t * T5_BINS;
             const int b = u & 1;
-            uint32_t c[KT];
+            uint32_t cw[KT / 2];                       // the count row as uint16 pairs (state 2i in the low half)
             if (t < nfull) {
                 mbar_wait_wd(&ld_full[g * 2 + b], ((uint32_t)(u >> 1)) & 1u);
-                const uint16_t* row = reinterpret_cast<const uint16_t*>(slabs + (g * 2 + b) * slab_bytes) + r * K;
-#pragma unroll
-                for (int s = 0; s < KT; ++s) c[s] = s < K ? (uint32_t)row[s] : 0u;
+                load_count_row<KT, KR>(reinterpret_cast<const uint16_t*>(slabs + (g * 2 + b) * slab_bytes) + r * K, K, cw);
             } else {
-                const bool live = bin0 + r < bins;
-                const uint16_t* row = cnt + (bin0 + r) * K;
-#pragma unroll
-                for (int s = 0; s < KT; ++s) c[s] = (live && s < K) ? (uint32_t)row[s] : 0u;
+                load_count_row_guarded<KT>(cnt + (bin0 + r) * K, K, bin0 + r < bins, cw);
             }
-            {
-                uint32_t cw[KT / 2];
-#pragma unroll
-                for (int i = 0; i < KT / 2; ++i) cw[i] = c[2 * i] | (c[2 * i + 1] << 16);
-                store_operand_row<KT>(a_row, r, cw, -1, 0u);        // the count row's bytes ARE the K-major A operand row
-            }
+            store_operand_row<KT>(a_row, r, cw, -1, 0u);        // the count row's bytes ARE the K-major A operand row
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -484,7 +411,7 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
             // work that does not need the accumulators: A = sum_s F[c_s]      (c = 0 for s >= K: F[0] = 0)
             double a = 0.0;
 #pragma unroll
-            for (int s = 0; s < KT; ++s) a += fh[c[s]].x;
+            for (int s = 0; s < KT; ++s) a += f1[(cw[s >> 1] >> (16 * (s & 1))) & 0xffffu];
             const double a_adj = a - cst;
 
             if (r == 0) bulk_wait_read0();             // the previous tile's rows have left the staging buffer
@@ -494,17 +421,22 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
 #pragma unroll
             for (int c0 = 0; c0 < 8 * KT; c0 += 32) {
                 uint32_t v[32];
-                double hg[4];
+                double2 tc[4];                         // {c HG[c], (double)c} of the four states of this column group
 #pragma unroll
-                for (int i = 0; i < 4; ++i) hg[i] = (c0 / 8 + i < KT) ? fh[c[c0 / 8 + i < KT ? c0 / 8 + i : 0]].y : 0.0;
+                for (int i = 0; i < 4; ++i) {
+                    const int tt = (c0 / 8 + i < KT) ? c0 / 8 + i : 0;
+                    tc[i] = t2[(cw[tt >> 1] >> (16 * (tt & 1))) & 0xffffu];
+                }
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);
+                float f[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int tt = c0 / 8 + i;
+                    f[i] = 0.0f;
                     if (tt < KT && (KR == 0 || tt < KR)) {
-                        // exact integer sum_s (c_s - [s==t]) M_st = H 2^32 + L, both halves as doubles via the magic bits
-                        // digits are < 2^22, so pairs combine in 32 bits; multipliers come from constant memory so
-                        // that they stay IMAD / IMAD.WIDE operands instead of being strength-reduced to shifts + adds
+                        // exact integer sum_s (c_s - [s==t]) M_st = H 2^32 + L, both halves as doubles via the magic bits.
+                        // Digits are < 2^22, so pairs combine in 32 bits; multipliers come from constant memory so that
+                        // they stay IMAD / IMAD.WIDE operands instead of being strength-reduced to shifts + adds.
                         const uint32_t t01 = mad_lo(v[8 * i + 1], c_k5tc.m8, v[8 * i]);
                         const uint32_t t23 = mad_lo(v[8 * i + 3], c_k5tc.m8, v[8 * i + 2]);
                         const uint32_t t45 = mad_lo(v[8 * i + 5], c_k5tc.m8, v[8 * i + 4]);
@@ -514,14 +446,21 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
                         const double dl = __longlong_as_double((long long)lb);                           // L + magic
                         const double dh = __longlong_as_double((long long)hb) - 6755399441055744.0;    // H
                         const double yd = fma(dh, 4294967296.0, dl);
-                        const double br = fma(yd, scale, a_adj) + hg[i];
-                        const double cd = __hiloint2double(0x43300000, (int)c[tt]) - 4503599627370496.0;
-                        const double val = fma(cd, br, 0.0);      // absent state: (+-0) + (+0) = +0.0 as in the reference
-                        if (KR != 0 || tt < K) {
-                            mystage[r * K + tt] = (float)val;
-                            if (WANT64 && bin0 + r < bins) out64[(bin0 + r) * K + tt] = val;
-                        }
+                        const double base = fma(yd, scale, a_adj);
+                        const double val = fma(tc[i].y, base, tc[i].x);   // absent state: 0 * base + (+0) = +0.0 as in the reference
+                        f[i] = (float)val;
+                        if (WANT64 && (KR != 0 || tt < K) && bin0 + r < bins) out64[(bin0 + r) * K + tt] = val;
                     }
+                }
+                if constexpr (KR != 0 && KR % 2 == 0) {
+                    // even row length: 8-byte stores (conflict-free at 72-byte row pitch)
+                    float2* dst = reinterpret_cast<float2*>(mystage + r * KR + c0 / 8);
+                    if (c0 / 8 < KR) dst[0] = make_float2(f[0], f[1]);
+                    if (c0 / 8 + 2 < KR) dst[1] = make_float2(f[2], f[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c0 / 8 + i < K) mystage[r * K + c0 / 8 + i] = f[i];
                 }
             }
             tc_fence_before();
@@ -560,11 +499,11 @@ static int launch_k5_tc2(const uint16_t* cnt, int64_t bins, int K, int width, in
     constexpr int NPAD = ((8 * KT + 31) / 32) * 32;
     auto kern = k5_s2_tc_kernel<KT, KR, NWG, WANT64>;
     const size_t smem = 1024 + (size_t)NWG * T5_A_BYTES + (size_t)NPAD * 128 + (size_t)NWG * 2 * T5_BINS * K * 2 +
-                        (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 1) * 16 + (size_t)(6 * NWG + 1) * 8 + 16;
+                        (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 1) * 16 + (size_t)(width + 2) * 8 +
+                        (size_t)(6 * NWG + 1) * 8 + 16;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + T5_BINS - 1) / T5_BINS;
-    kern<<<persistent_grid(ntiles, 1), NWG * 128 + 64, smem, st>>>(cnt, (long long)bins, K, width, (double)perms, ws, o32, o64,
-                                                                    getenv("EPI_K5_DBG") ? atoi(getenv("EPI_K5_DBG")) : 0);
+    kern<<<persistent_grid(ntiles, 1), NWG * 128 + 64, smem, st>>>(cnt, (long long)bins, K, width, (double)perms, ws, o32, o64);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -588,7 +527,6 @@ static int launch_k5_tc(const uint16_t* cnt, int64_t bins, int K, int width, int
 int scores_s2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
                  float* o32, double* o64, cudaStream_t st) {
     if (K == 18) return launch_k5_tc<18, 18, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
-    if (K == 15 && getenv("EPI_K5_NWG3")) return launch_k5_tc<16, 15, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K == 15) return launch_k5_tc<16, 15, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K <= 16) return launch_k5_tc<16, 0, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K <= 18) return launch_k5_tc<18, 0, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);

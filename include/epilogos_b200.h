@@ -48,7 +48,8 @@ int epi_bin_counts(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitc
  * n1[s]    += sum_b cnt[b][s]                                   (expected.py:106-113, s1Calc)
  * n2[s][t] += sum_b cnt[b][s]*cnt[b][t] - [s==t]*cnt[b][s]      (expected.py:146-158, s2Calc)
  * Accumulates into int64 device arrays (caller zeroes them); either pointer may be NULL.
- * `width` = biosamples per row (upper bound of a count). */
+ * `width` = biosamples per row (upper bound of a count).
+ * Runs as a Gram update of the count bytes on the tensor cores (tcgen05.mma kind::i8, exact int32 accumulation). */
 int epi_expected_s1s2(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width,
                       int64_t* n1_dev, int64_t* n2_dev, void* stream);
 
@@ -60,13 +61,15 @@ int epi_normalize_i64(const int64_t* counts_dev, int64_t n, float* out_dev, void
  * S1: score[b][s] = o*log2(o/E1[s]), o = cnt[b][s]/width        (scores.py:339-344, 317, 550)
  * S2: score[b][t] = sum_s o_st*log2(o_st/E2[s][t]) added in order s = 0..K-1,
  *     o_st = (cnt_s*cnt_t - [s==t]cnt_s)/perms                  (scores.py:443-451, 412, 550)
- *     `width` = biosamples per row (upper bound of a count); `perms` = C*(C-1) of the group the
- *     observation is normalised with (they differ only for the -g quirk of scores.py:397-398).
+ *     `width` = labels per row = the sum of a row's counts (every row has exactly this many); `perms` = C*(C-1)
+ *     of the group the observation is normalised with (they differ only for the -g quirk of scores.py:397-398).
  * Terms with o == 0 or E == 0 are 0 (numpy.ma masking of klScoreND).
  * out32 (float32, the reference's stored dtype) and/or out64 (unrounded float64) may be NULL.
  * mode: EPI_SCORE_TABLE evaluates log2 through tables of log2(count) and log2(E) (default, within
- *       1e-9 relative + 1e-12 absolute of the float64 reference); EPI_SCORE_DIRECT evaluates
- *       obs*log2(obs/E) term by term with a correctly rounded divide (verification path). */
+ *       1e-9 relative + 1e-12 absolute of the float64 reference; for S2 the K x K mat-vec against log2 E runs on the
+ *       tensor cores with log2 E in 56-bit fixed point, i.e. exactly); EPI_SCORE_DIRECT evaluates
+ *       obs*log2(obs/E) term by term with a correctly rounded divide (verification path, and the path taken
+ *       automatically when the expected table has zero entries). */
 #define EPI_SCORE_TABLE 0
 #define EPI_SCORE_DIRECT 1
 int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width,

@@ -183,11 +183,16 @@ def test_full_real_chr1_against_reference(eng, golden):
         ref = orc.s1_scores(x, k, exp) if sal == 1 else orc.s2_scores(x, k, exp)
         assert_f32_close(sc, ref)
         assert_f32_close(sc[:2000], g["s%d_scores_head" % sal])
-        scores[sal] = sc
+        scores[sal] = sc.copy()          # single_host reuses one pinned result buffer per shape
     starts = np.arange(len(x), dtype=np.int64) * 200
     sel = roi.max_mean(starts, starts + 200, scores[1].sum(axis=1), 50, 100)
     assert np.array_equal(sel["original_idx"], g["roi_original_idx"])
     assert np.array_equal(sel["start"], g["roi_start"]) and np.array_equal(sel["end"], g["roi_end"])
+    # S2: same regions, same order as the selection made from the oracle's scores
+    ref2 = orc.s2_scores(x, k, g["s2_exp"])
+    want = roi.max_mean(starts, starts + 200, ref2.sum(axis=1), 50, 100)
+    got = roi.max_mean(starts, starts + 200, scores[2].sum(axis=1), 50, 100)
+    assert np.array_equal(got["original_idx"], want["original_idx"])
 
 
 # -------------------------------------------------------------------------------- full-size properties
