@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one synthetic matrix that is already resident in HBM:
-K1 counts -> K2 expected table -> (allreduce over ranks) -> K4 normalise -> K5 scores.
+K1 counts -> K2 expected table (tensor-core Gram of the count bytes) -> (allreduce over ranks) -> K4 normalise ->
+K5 scores (S2: table preparation + tensor-core mat-vec kernel + the gated DIRECT fallback = 6 launches per step).
 Workload at every N: BASELINE.json configs[1], S2 on 15.5 M bins x 833 biosamples x 18 states PER GPU
 (weak scaling; the bins shard with no data-path collective, only the 18x18 table is all-reduced).
 The matrix (13 GB) is far larger than L2 (126 MB), so no L2 flush is needed between steps.
@@ -333,7 +334,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": bins * cols, "ms_per_launch": k1_ms},
             "step_roofline": {"algorithmic_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                               "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
-            "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": 6 * args.steps, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_baseline(cols, k, saliency)

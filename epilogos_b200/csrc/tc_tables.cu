@@ -297,8 +297,8 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
     uint8_t* b_op = a_ops + NWG * T5_A_BYTES;                                // NPAD x 128 B
     uint8_t* slabs = b_op + NPAD * 128;                                      // NWG x 2 x slab_bytes
     float* stage = reinterpret_cast<float*>(slabs + NWG * 2 * slab_bytes);   // NWG x 128 x K
-    double2* t2 = reinterpret_cast<double2*>(stage + NWG * T5_BINS * K);     // width + 1 entries {c HG[c], (double)c}
-    double* f1 = reinterpret_cast<double*>(t2 + width + 1);                  // width + 1 entries F[c] (+1 pad)
+    double* g1 = reinterpret_cast<double*>(stage + NWG * T5_BINS * K);       // width + 1 entries c HG[c] (+1 pad)
+    double* f1 = g1 + ((width + 2) & ~1);                                    // width + 1 entries F[c] (+1 pad)
     uint64_t* ld_full = reinterpret_cast<uint64_t*>(f1 + ((width + 2) & ~1)); // [NWG][2]
     uint64_t* ld_empty = ld_full + NWG * 2;
     uint64_t* a_full = ld_empty + NWG * 2;                                   // [NWG]
@@ -314,17 +314,14 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
     for (int i = tid; i < NWG * T5_A_BYTES / 16; i += NT) reinterpret_cast<uint4*>(a_ops)[i] = make_uint4(0u, 0u, 0u, 0u);
     {
         // F[c] = c log2(c) / P,  HG[c] = ((log2 c - log2 P)(W - 1) - c log2 c + (c-1) log2(c-1)) / P      (scores.cu header)
-        // score_t = c_t (base_t + HG[c_t]) = fma(c_t, base_t, c_t HG[c_t]): the table holds c HG[c] and c as a double
+        // score_t = c_t (base_t + HG[c_t]) = fma(c_t, base_t, c_t HG[c_t]): the second table holds c HG[c]
         const double lp = log2(perms), invp = 1.0 / perms, wm1 = (double)width - 1.0;
         for (int c = tid; c <= width; c += NT) {
             const double l = c > 0 ? log2((double)c) : 0.0;
             const double l1 = c > 1 ? log2((double)(c - 1)) : 0.0;
             const double cl = (double)c * l;
             f1[c] = cl * invp;
-            double2 v;
-            v.x = (double)c * ((fma(l - lp, wm1, -cl) + (double)(c > 0 ? c - 1 : 0) * l1) * invp);
-            v.y = (double)c;
-            t2[c] = v;
+            g1[c] = (double)c * ((fma(l - lp, wm1, -cl) + (double)(c > 0 ? c - 1 : 0) * l1) * invp);
         }
     }
     fence_proxy_async_smem();
@@ -385,7 +382,7 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
         uint8_t* a_row = a_ops + g * T5_A_BYTES + r * 128;
         float* mystage = stage + g * T5_BINS * K;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * NPAD);
-        const double scale = c_k5tc.scale, cst = c_k5tc.cst;
+        const double scale = c_k5tc.scale, cst = c_k5tc.cst, scale32 = c_k5tc.scale * 4294967296.0;
         int u = 0;
         for (long long t = blockIdx.x + (long long)g * gridDim.x; t < ntiles; t += (long long)NWG * gridDim.x, ++u) {
             const long long bin0 = t * T5_BINS;
@@ -409,10 +406,10 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
             }
 
             // work that does not need the accumulators: A = sum_s F[c_s]      (c = 0 for s >= K: F[0] = 0)
-            double a = 0.0;
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};       // four partial sums: the adds are ~20-cycle dependent fp64 operations
 #pragma unroll
-            for (int s = 0; s < KT; ++s) a += f1[(cw[s >> 1] >> (16 * (s & 1))) & 0xffffu];
-            const double a_adj = a - cst;
+            for (int s = 0; s < KT; ++s) a4[s & 3] += f1[(cw[s >> 1] >> (16 * (s & 1))) & 0xffffu];
+            const double a_adj = ((a4[0] + a4[1]) + (a4[2] + a4[3])) - cst;
 
             if (r == 0) bulk_wait_read0();             // the previous tile's rows have left the staging buffer
             named_barrier(1 + g, 128);
@@ -421,11 +418,13 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
 #pragma unroll
             for (int c0 = 0; c0 < 8 * KT; c0 += 32) {
                 uint32_t v[32];
-                double2 tc[4];                         // {c HG[c], (double)c} of the four states of this column group
+                double chg[4], cd[4];                  // c HG[c] and c (as a double, via the 2^52 bit pattern) of the four states
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int tt = (c0 / 8 + i < KT) ? c0 / 8 + i : 0;
-                    tc[i] = t2[(cw[tt >> 1] >> (16 * (tt & 1))) & 0xffffu];
+                    const uint32_t ct = (cw[tt >> 1] >> (16 * (tt & 1))) & 0xffffu;
+                    chg[i] = g1[ct];
+                    cd[i] = __hiloint2double(0x43300000, (int)ct) - 4503599627370496.0;
                 }
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);
                 float f[4];
@@ -445,9 +444,9 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
                         const unsigned long long hb = mad_wide(t67, c_k5tc.m16, c_k5tc.ch[tt]) + (unsigned long long)t45;
                         const double dl = __longlong_as_double((long long)lb);                           // L + magic
                         const double dh = __longlong_as_double((long long)hb) - 6755399441055744.0;    // H
-                        const double yd = fma(dh, 4294967296.0, dl);
-                        const double base = fma(yd, scale, a_adj);
-                        const double val = fma(tc[i].y, base, tc[i].x);   // absent state: 0 * base + (+0) = +0.0 as in the reference
+                        // base = (H 2^32 + L) scale + a_adj, with the L part off the dependent chain of the H conversion
+                        const double base = fma(dh, scale32, fma(dl, scale, a_adj));
+                        const double val = fma(cd[i], base, chg[i]);      // absent state: 0 * base + (+0) = +0.0 as in the reference
                         f[i] = (float)val;
                         if (WANT64 && (KR != 0 || tt < K) && bin0 + r < bins) out64[(bin0 + r) * K + tt] = val;
                     }
@@ -499,7 +498,7 @@ static int launch_k5_tc2(const uint16_t* cnt, int64_t bins, int K, int width, in
     constexpr int NPAD = ((8 * KT + 31) / 32) * 32;
     auto kern = k5_s2_tc_kernel<KT, KR, NWG, WANT64>;
     const size_t smem = 1024 + (size_t)NWG * T5_A_BYTES + (size_t)NPAD * 128 + (size_t)NWG * 2 * T5_BINS * K * 2 +
-                        (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 1) * 16 + (size_t)(width + 2) * 8 +
+                        (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 2) * 16 +
                         (size_t)(6 * NWG + 1) * 8 + 16;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + T5_BINS - 1) / T5_BINS;
