@@ -155,54 +155,69 @@ def run_reference(args):
 # clocks sampling through NVML while the timed region runs
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-               0x80: "hw_power_brake_slowdown"}
+    """SM clock / throttle reasons of one GPU while the timed region runs, taken by a SEPARATE `nvidia-smi -lms` process
+    (the recipe's clocks line).  An in-process NVML poller was measured to cost 0.25 ms per 3 ms step at 2 GPUs: its
+    driver calls serialise with rank 0's kernel launches and the other rank then waits at the all-reduce."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_power_brake_slowdown")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap", "hw_power_brake_slowdown"]
 
     def __init__(self, index):
-        self.samples, self.reasons, self.power = [], set(), []
-        self.stop_flag = False
-        self.max_mhz = None
+        import subprocess
+        import tempfile
+        self.t_lo = self.t_hi = None
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        period = os.environ.get("EPI_BENCH_CLOCK_PERIOD_MS", "20")
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-        self.thread = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        # NVML queries take driver locks that can delay kernel launches on the sampled GPU, so the loop is kept light:
-        # SM clock every `period` ms, throttle reasons and power every 5th sample.
-        nv = self.nv
-        period = float(os.environ.get("EPI_BENCH_CLOCK_PERIOD_MS", "10")) * 1e-3
-        i = 0
-        while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                if i % 5 == 0:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    for bit, name in self.REASONS.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-            except Exception:
-                pass
-            i += 1
-            time.sleep(period)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", period],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
 
     def start(self):
-        if self.nv is not None:
-            self.thread.start()
+        """Call right before the timed region (the process is already sampling)."""
+        self.t_lo = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.nv is not None and self.thread.is_alive():
-            self.thread.join()
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s), "power_w_max": max(self.power) if self.power else None}
+        self.t_hi = time.time()
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "power_w_max": None}
+        time.sleep(0.03)                     # let the sample that straddles the end land
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        import datetime
+        rows = []
+        for line in self.out.read().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) != 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, int(float(f[1])), int(float(f[2])), float(f[3]), [x.lower().startswith("active") for x in f[4:]]))
+            except ValueError:
+                continue
+        self.out.close()
+        try:
+            os.unlink(self.out.name)
+        except OSError:
+            pass
+        inside = [r for r in rows if self.t_lo - 0.005 <= r[0] <= self.t_hi + 0.005]
+        if not inside and rows:              # region shorter than the sampling period: take the nearest sample
+            mid = 0.5 * (self.t_lo + self.t_hi)
+            inside = [min(rows, key=lambda r: abs(r[0] - mid))]
+        clk = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n, on in zip(self.NAMES, r[4]) if on})
+        return {"sm_mhz": clk[len(clk) // 2] if clk else None, "sm_max_mhz": inside[0][2] if inside else None,
+                "reasons": reasons, "samples": len(inside), "power_w_max": max((r[3] for r in inside), default=None),
+                "how": "nvidia-smi -lms %s in a separate process, samples inside the timed region" %
+                       os.environ.get("EPI_BENCH_CLOCK_PERIOD_MS", "20")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -252,26 +267,34 @@ def run_ours(args):
             engine.scores_s2(cnt, cols, e, out32=scores)
         return e
 
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("EPI_BENCH_NO_CLOCKS") else None
     for _ in range(max(3, args.warmup)):
+        step(False)
+    torch.cuda.synchronize()
+    if rank == 0:
+        time.sleep(0.3)                      # nvidia-smi needs a moment to start sampling
+    if world > 1:
+        dist.barrier()
+    for _ in range(3):                       # every rank: back under load after the pause (collectives stay matched)
         step(False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(stream)
     for _ in range(args.steps):
-        step(True)
+        step(not os.environ.get("EPI_BENCH_NO_K1_EVENTS"))
     t1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if sampler else None
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
-    k1_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k1_ev) / len(k1_ev)], device="cuda", dtype=torch.float64)
+    k1_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k1_ev) / max(1, len(k1_ev)) if k1_ev else 1.0], device="cuda",
+                         dtype=torch.float64)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(k1_ms, op=dist.ReduceOp.MAX)
@@ -373,11 +396,11 @@ def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, de
         engine.scores_s3(x, cols, k, terms, out32=scores)
 
     steps = min(args.steps, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
     step(False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
