@@ -233,6 +233,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        from epilogos_b200 import dist as edist
+        edist.bind_to_gpu_numa(local)          # pinned host buffers and copies on the GPU's own socket
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     bins, cols, k, desc = CONFIGS[args.config]
     if args.bins:

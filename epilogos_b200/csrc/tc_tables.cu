@@ -28,13 +28,13 @@ namespace epi {
 // read K-major is the A operand of the score kernel below.  Byte column 2K of every row is 1 (the N1 column).
 // ================================================================================================
 constexpr int T2_BINS = 128;          // bins per tile
-constexpr int T2_STAGES = 6;          // count-tile ring (1D bulk copies)
+constexpr int T2_STAGES = 4;          // count-tile ring (1D bulk copies)
 constexpr int T2_OPS = 2;             // operand buffers
 constexpr int T2_THREADS = 192;       // warps 0-3 build operand rows, warp 4 = copy producer, warp 5 = MMA issuer
 constexpr int T2_TMEM_COLS = 128;
 
 template <int KT, int KR>
-__global__ void __launch_bounds__(T2_THREADS, 3)
+__global__ void __launch_bounds__(T2_THREADS, 4)
 k2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, unsigned long long* __restrict__ n1,
              unsigned long long* __restrict__ n2) {
     const int K = KR ? KR : Krt;
@@ -167,7 +167,7 @@ static int launch_k2_tc_impl(const uint16_t* cnt, int64_t bins, int K, int64_t* 
     auto kern = k2_tc_kernel<KT, KR>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + T2_BINS - 1) / T2_BINS;
-    int ctas = 3;          // measured at 15.5 M bins x 18 states: 0.33 / 0.22 / 0.19 ms with 1 / 2 / 3 CTAs per SM
+    int ctas = 4;          // measured at 15.5 M bins x 18 states: 0.33 / 0.22 / 0.19 ms at 1 / 2 / 3 CTAs per SM (6 stages), 0.185 at 4 (4 stages)
     if (const char* e = getenv("EPI_K2TC_CTAS")) ctas = atoi(e) > 0 ? atoi(e) : ctas;      // tuning knob
     kern<<<persistent_grid(ntiles, ctas), T2_THREADS, smem, st>>>(cnt, (long long)bins, K,
                                                                 reinterpret_cast<unsigned long long*>(n1),
@@ -206,8 +206,7 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 struct K5TcConsts {
-    unsigned long long cl[EPI_MAX_STATES];      // MAGIC - (M_tt mod 2^32)   (the [s==t] term, folded into the integer sum)
-    unsigned long long ch[EPI_MAX_STATES];      // MAGIC - (M_tt div 2^32)
+    double dg[EPI_MAX_STATES];                  // M_tt 2^-F / perms / 8: the [s==t] term of y_t (see `base` in the kernel)
     double scale;                               // 2^-F / perms
     double cst;                                 // (2^52 + 2^51) * scale
     int has_zero;
@@ -259,11 +258,7 @@ __global__ void k5tc_prepare_kernel(const float* __restrict__ e, int K, double p
         const uint32_t n = (uint32_t)(t * 8 + dd + h), k = (uint32_t)(2 * s + h);
         b_image[sw128_offset(n, k)] = (uint8_t)((mfix[st] >> (8 * dd)) & 255ull);
     }
-    if (threadIdx.x < K) {
-        const unsigned long long mtt = mfix[threadIdx.x * K + threadIdx.x];
-        out->cl[threadIdx.x] = T5_MAGIC - (mtt & 0xffffffffull);
-        out->ch[threadIdx.x] = T5_MAGIC - (mtt >> 32);
-    }
+    if (threadIdx.x < K) out->dg[threadIdx.x] = ldexp((double)mfix[threadIdx.x * K + threadIdx.x], -F - 3) / perms;
     if (threadIdx.x == 0) {
         const double scale = ldexp(1.0, -F) / perms;
         out->scale = scale;
@@ -382,7 +377,8 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
         uint8_t* a_row = a_ops + g * T5_A_BYTES + r * 128;
         float* mystage = stage + g * T5_BINS * K;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * NPAD);
-        const double scale = c_k5tc.scale, cst = c_k5tc.cst, scale32 = c_k5tc.scale * 4294967296.0;
+        // everything that multiplies the count is kept divided by 8: the count enters as the double 8 c (its table byte offset)
+        const double scale = c_k5tc.scale * 0.125, cst = c_k5tc.cst, scale32 = c_k5tc.scale * (4294967296.0 * 0.125);
         int u = 0;
         for (long long t = blockIdx.x + (long long)g * gridDim.x; t < ntiles; t += (long long)NWG * gridDim.x, ++u) {
             const long long bin0 = t * T5_BINS;
@@ -406,25 +402,30 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
             }
 
             // work that does not need the accumulators: A = sum_s F[c_s]      (c = 0 for s >= K: F[0] = 0)
+            // byte offsets c_s * 8 into the two look-up tables, extracted once (both tables are indexed by the same counts)
+            uint32_t co[KT];
+#pragma unroll
+            for (int s = 0; s < KT; ++s) co[s] = ((cw[s >> 1] >> (16 * (s & 1))) & 0xffffu) << 3;
             double a4[4] = {0.0, 0.0, 0.0, 0.0};       // four partial sums: the adds are ~20-cycle dependent fp64 operations
 #pragma unroll
-            for (int s = 0; s < KT; ++s) a4[s & 3] += f1[(cw[s >> 1] >> (16 * (s & 1))) & 0xffffu];
-            const double a_adj = ((a4[0] + a4[1]) + (a4[2] + a4[3])) - cst;
+            for (int s = 0; s < KT; ++s) a4[s & 3] += *reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(f1) + co[s]);
+            const double a_adj = (((a4[0] + a4[1]) + (a4[2] + a4[3])) - cst) * 0.125;
 
-            if (r == 0) bulk_wait_read0();             // the previous tile's rows have left the staging buffer
-            named_barrier(1 + g, 128);
+            // the warp's 32 rows of the previous tile have left the staging buffer (each warp stages and stores its own rows:
+            // no warpgroup-wide barrier anywhere in the loop, the four warps only meet at the a_full / mma_done mbarriers)
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
             mbar_wait_wd(&mma_done[g], ((uint32_t)u) & 1u);
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < 8 * KT; c0 += 32) {
                 uint32_t v[32];
-                double chg[4], cd[4];                  // c HG[c] and c (as a double, via the 2^52 bit pattern) of the four states
+                double chg[4], cd[4];                  // c HG[c] and 8 c (as a double, via the 2^52 bit pattern) of the four states
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int tt = (c0 / 8 + i < KT) ? c0 / 8 + i : 0;
-                    const uint32_t ct = (cw[tt >> 1] >> (16 * (tt & 1))) & 0xffffu;
-                    chg[i] = g1[ct];
-                    cd[i] = __hiloint2double(0x43300000, (int)ct) - 4503599627370496.0;
+                    chg[i] = *reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(g1) + co[tt]);
+                    cd[i] = __hiloint2double(0x43300000, (int)co[tt]) - 4503599627370496.0;         // 8 c, exactly
                 }
                 tmem_ld_32x32(taddr + (uint32_t)c0, v);
                 float f[4];
@@ -440,12 +441,13 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
                         const uint32_t t23 = mad_lo(v[8 * i + 3], c_k5tc.m8, v[8 * i + 2]);
                         const uint32_t t45 = mad_lo(v[8 * i + 5], c_k5tc.m8, v[8 * i + 4]);
                         const uint32_t t67 = mad_lo(v[8 * i + 7], c_k5tc.m8, v[8 * i + 6]);
-                        const unsigned long long lb = mad_wide(t23, c_k5tc.m16, c_k5tc.cl[tt]) + (unsigned long long)t01;
-                        const unsigned long long hb = mad_wide(t67, c_k5tc.m16, c_k5tc.ch[tt]) + (unsigned long long)t45;
+                        // {t01, magic_hi} is a register pair (no instruction): L + magic = t23 2^16 + that pair
+                        const unsigned long long lb = mad_wide(t23, c_k5tc.m16, ((unsigned long long)(T5_MAGIC >> 32) << 32) | t01);
+                        const unsigned long long hb = mad_wide(t67, c_k5tc.m16, ((unsigned long long)(T5_MAGIC >> 32) << 32) | t45);
                         const double dl = __longlong_as_double((long long)lb);                           // L + magic
                         const double dh = __longlong_as_double((long long)hb) - 6755399441055744.0;    // H
-                        // base = (H 2^32 + L) scale + a_adj, with the L part off the dependent chain of the H conversion
-                        const double base = fma(dh, scale32, fma(dl, scale, a_adj));
+                        // base = (H 2^32 + L) scale + A - [s==t] term, with the L part off the dependent chain of the H conversion
+                        const double base = fma(dh, scale32, fma(dl, scale, a_adj)) - c_k5tc.dg[tt];
                         const double val = fma(cd[i], base, chg[i]);      // absent state: 0 * base + (+0) = +0.0 as in the reference
                         f[i] = (float)val;
                         if (WANT64 && (KR != 0 || tt < K) && bin0 + r < bins) out64[(bin0 + r) * K + tt] = val;
@@ -464,20 +466,22 @@ k5_s2_tc_kernel(const uint16_t* __restrict__ cnt, long long bins, int Krt, int w
             }
             tc_fence_before();
             fence_proxy_async_smem();
-            named_barrier(1 + g, 128);
+            __syncwarp();
             if (out32 != nullptr) {
+                const int wq = warp & 3;
+                const long long wbin0 = bin0 + 32 * wq;
                 if (t < nfull) {
-                    if (r == 0) {
-                        bulk_store_1d(out32 + bin0 * K, mystage, (uint32_t)(T5_BINS * K * 4));
+                    if (lane == 0) {
+                        bulk_store_1d(out32 + wbin0 * K, mystage + 32 * wq * K, (uint32_t)(32 * K * 4));
                         bulk_commit();
                     }
-                } else {
-                    const int n = (int)(bins - bin0) * K;
-                    for (int i = r; i < n; i += 128) out32[bin0 * K + i] = mystage[i];
+                } else if (wbin0 < bins) {
+                    const int n = (int)((bins - wbin0) < 32 ? (bins - wbin0) : 32) * K;
+                    for (int i = lane; i < n; i += 32) out32[wbin0 * K + i] = mystage[32 * wq * K + i];
                 }
             }
         }
-        if (r == 0) bulk_wait0();
+        if (lane == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();

@@ -47,3 +47,26 @@ def gather_rows(t, total_rows, dst=0):
 def barrier():
     if initialised():
         dist.barrier()
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (one per GPU) to the CPUs that are NUMA-local to its GPU, so that the pinned host buffers it
+    allocates afterwards (first touch) and its H2D / D2H copies stay on the GPU's own socket.  With several ranks streaming
+    13 GB matrices over PCIe at once, remote-socket buffers cost end-to-end bandwidth.  Best effort: returns the CPU list or
+    None when NVML or the affinity call is not available."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None

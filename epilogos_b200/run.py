@@ -167,6 +167,8 @@ def main(mode, commandLineBool, inputDirectory, inputDirectory1, inputDirectory2
     launched = "RANK" in os.environ and "WORLD_SIZE" in os.environ
     if launched and not td.is_initialized():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        from . import dist as _dist
+        _dist.bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))
         td.init_process_group("nccl")
     from . import dist, expected, expectedCombination, scores
     lead = dist.rank() == 0

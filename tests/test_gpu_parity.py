@@ -135,6 +135,35 @@ def test_other_state_models(eng, k, cols):
                                    rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("bins,cols,k", [
+    (1, 2, 1), (127, 255, 18), (128, 256, 18), (129, 257, 15), (256, 1023, 7), (300, 2047, 18), (300, 2048, 18),
+    (4097, 5000, 4), (640, 65, 31), (33_000, 70, 32), (1000, 833, 2)])
+def test_tensor_core_tables_and_scores_edge_shapes(eng, bins, cols, k):
+    """K2 / K5-S2 on the tensor cores at the edges of their tiling: fewer bins than one 128-bin tile, exact tile
+    multiples, counts that do / do not need the high byte (255 / 256 biosamples), the widest table-driven width (2047) and
+    the first width that takes the per-bin path (2048), an accumulator drain in mid-run (33 000 bins), odd state counts."""
+    rng = np.random.default_rng(bins * 7 + cols * 3 + k)
+    x = rng.integers(0, k, size=(bins, cols)).astype(np.int8)
+    if bins > 2:
+        x[1, :] = k - 1                      # a bin with a single state: count = cols (largest possible count)
+    cnt = eng.bin_counts(dev_states(eng, x), cols, k)
+    n1, n2 = eng.expected_tables(cnt, cols)
+    assert np.array_equal(n1.cpu().numpy(), orc.s1_expected_counts(x, k))
+    assert np.array_equal(n2.cpu().numpy(), orc.s2_expected_counts(x, k))
+    n2h = n2.cpu().numpy().copy()
+    n2h[n2h == 0] = 1                        # a table without zeros keeps the tensor-core path (zeros -> DIRECT, tested above)
+    e2 = orc.normalize_expected(n2h)
+    s32, s64 = eng.scores_s2(cnt, cols, torch.from_numpy(e2).cuda(), want64=True)
+    ref = orc.s2_scores(x, k, e2, np.float64)
+    np.testing.assert_allclose(s64.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(s32.cpu().numpy(), s64.cpu().numpy().astype(np.float32))
+    e1 = orc.normalize_expected(orc.s1_expected_counts(x, k))
+    t32, t64 = eng.scores_s1(cnt, cols, torch.from_numpy(e1).cuda(), want64=True)
+    ref1 = orc.s1_scores(x, k, e1, np.float64)
+    np.testing.assert_allclose(t64.cpu().numpy(), ref1, rtol=RTOL, atol=ATOL)
+    assert_f32_close(t32.cpu().numpy(), ref1.astype(np.float32), max_ulp_frac=1e-4)
+
+
 def test_foreign_expected_table_with_zeros_is_masked(eng):
     """klScoreND masks terms whose expected frequency is 0 (scores.py:550); a table computed from other
     data can have zeros where this data has observations."""
