@@ -19,6 +19,8 @@
  *     Labels must be < num_states (the packer validates; the reference would raise IndexError).
  *   - per-bin state counts are uint16 [bins][num_states] (a count is <= biosamples <= 65535).
  *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is present.
+ *   - the score entry points keep small per-device tables (constant memory, a scratch buffer); calls for one device
+ *     must be stream-ordered with respect to each other (one stream, or events between streams).
  */
 #ifndef EPILOGOS_B200_H
 #define EPILOGOS_B200_H
