@@ -18,6 +18,15 @@
 //   * labels come from a transposed copy xT[C][bins] so a thread's BPT labels of biosample i are one coalesced load;
 //   * per-bin score rows live in shared memory and are written once: no atomics, deterministic summation order.
 // T is streamed once per CTA: L2->SM traffic = (bins / BC) * 1.8 GB.
+//
+// Symmetry (version 3): the expected table of s3Calc is symmetric, E3[i][j][a][c] == E3[j][i][c][a], hence so are the
+// terms, and the ordered pairs (i,j) and (j,i) of a bin contribute the SAME value -- once to the bucket of x_j, once to
+// the bucket of x_i.  The SYM kernel walks only i < j: one look-up per UNORDERED pair, added to the j accumulator in
+// registers and, summed over the j-block, to the score row of x_i in shared memory: half the look-ups (the limiter) and
+// half the slab traffic.  s3_symmetry_kernel verifies the property on the device for every table it is given (a foreign
+// exp_freq file need not have it); both kernels are queued and the one that does not apply exits at once.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace epi {
@@ -64,16 +73,45 @@ __global__ void __launch_bounds__(256) s3_transpose_kernel(const int8_t* __restr
     }
 }
 
-template <int BPT, int JC>
+// *flag = 0 if some T[i][j][a][c] != T[j][i][c][a] (bit pattern compare; the flag is preset to non-zero by the caller)
+__global__ void __launch_bounds__(256) s3_symmetry_kernel(const double* __restrict__ terms, int cols, int K,
+                                                          int* __restrict__ flag) {
+    const long long blk = s3_block_stride(K);
+    const long long kk = (long long)K * K;
+    const long long n = (long long)cols * cols * kk;
+    bool bad = false;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long pair = idx / kk;
+        const int r = (int)(idx - pair * kk);
+        const int i = (int)(pair / cols), j = (int)(pair - (long long)i * cols);
+        if (i < j) {
+            const int a = r / K, c = r - a * K;
+            const long long v = __double_as_longlong(terms[pair * blk + r]);
+            const long long w = __double_as_longlong(terms[((long long)j * cols + i) * blk + (long long)c * K + a]);
+            bad |= v != w;
+        }
+    }
+    if (bad) *flag = 0;
+}
+
+// SYM: 0 = all ordered pairs (any table), 1 = unordered pairs of a symmetric table.  *gate != 0 means symmetric: only the
+// kernel that applies does the work, the other one exits at once.
+template <int BPT, int JC, int SYM>
 __global__ void __launch_bounds__(S3S_THREADS + 32, 1)
 s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, int cols, int K,
-                const double* __restrict__ terms, float* __restrict__ out32, double* __restrict__ out64) {
+                const double* __restrict__ terms, const int* __restrict__ gate, float* __restrict__ out32,
+                double* __restrict__ out64) {
+    if ((*gate != 0) != (SYM != 0)) return;
     constexpr int BC = S3S_THREADS * BPT;
     extern __shared__ __align__(128) uint8_t smem[];
     const int blk = (int)s3_block_stride(K);
     const int slab_bytes = JC * blk * 8;
-    double* sc = reinterpret_cast<double*>(smem);                                   // [BC][K]
-    uint8_t* slabs = smem + (((size_t)BC * K * 8 + 127) & ~(size_t)127);           // 2 slabs
+    // score rows: sc[(u * 256 + tid) * KP + state], KP odd, so that the lanes of a warp hit different banks when they
+    // update the same state (the SYM kernel read-modify-writes one row entry per bin and slab)
+    const int KP = K | 1;
+    double* sc = reinterpret_cast<double*>(smem);                                   // [BPT][256][KP]
+    uint8_t* slabs = smem + (((size_t)BC * KP * 8 + 127) & ~(size_t)127);          // 2 slabs
     uint64_t* full = reinterpret_cast<uint64_t*>(slabs + 2 * (size_t)slab_bytes);
     uint64_t* empty = full + 2;
 
@@ -86,7 +124,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < BC * K; i += blockDim.x) sc[i] = 0.0;
+    for (int i = tid; i < BC * KP; i += blockDim.x) sc[i] = 0.0;
     __syncthreads();
 
     const int njb = (cols + JC - 1) / JC;
@@ -96,7 +134,8 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
             int s = 0;
             uint32_t ph = 0;
             for (int jb = 0; jb < njb; ++jb) {
-                for (int i = 0; i < cols; ++i) {
+                const int iend = SYM ? ((jb + 1) * JC < cols ? (jb + 1) * JC : cols) : cols;
+                for (int i = 0; i < iend; ++i) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], slab_bytes);
                     bulk_load_1d(slabs + (size_t)s * slab_bytes, terms + ((long long)i * cols + jb * JC) * blk,
@@ -114,7 +153,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
     // ---------------- consumers: BPT bins per thread ----------------
     const long long bin0 = (long long)blockIdx.x * BC + (long long)tid * BPT;
     const uint8_t* col = xt + bin0;                          // + i * bp
-    double* my_sc = sc + (size_t)tid * BPT * K;
+    double* my_sc = sc + (size_t)tid * KP;                  // + u * 256 * KP
     const uint32_t slab0 = smem_u32(slabs);
     int s = 0;
     uint32_t ph = 0;
@@ -150,15 +189,36 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
         }
         uint32_t nxt[BPT];
         load_labels(0, nxt);
-        for (int i = 0; i < cols; ++i) {
-            uint32_t a[BPT];
+        const int iend = SYM ? (j0 + JC < cols ? j0 + JC : cols) : cols;
+        const int njv = cols - j0 < JC ? cols - j0 : JC;          // biosamples of this j-block that exist
+        for (int i = 0; i < iend; ++i) {
+            uint32_t a[BPT], ai[BPT];
 #pragma unroll
-            for (int u = 0; u < BPT; ++u) a[u] = nxt[u] * (uint32_t)(K * 8);
-            if (i + 1 < cols) load_labels(i + 1, nxt);          // prefetch the next biosample's labels
+            for (int u = 0; u < BPT; ++u) {
+                ai[u] = nxt[u];
+                a[u] = nxt[u] * (uint32_t)(K * 8);
+            }
+            if (i + 1 < iend) load_labels(i + 1, nxt);          // prefetch the next biosample's labels
             mbar_wait(&full[s], ph);
             const uint32_t base = slab0 + (uint32_t)s * (uint32_t)slab_bytes;
             const bool diag = (i >= j0) && (i < j0 + JC);
-            if (!diag) {
+            if (SYM) {
+                // unordered pairs i < j: the term goes to the bucket of x_j (registers) and to the bucket of x_i (score row)
+#pragma unroll
+                for (int u = 0; u < BPT; ++u) {
+                    double si = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < JC; ++jj) {
+                        if (jj < njv && (!diag || j0 + jj > i)) {      // real biosample, and j > i inside the diagonal block
+                            double t;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
+                            acc[u][jj] += t;
+                            si += t;
+                        }
+                    }
+                    my_sc[(size_t)u * S3S_THREADS * KP + ai[u]] += si;
+                }
+            } else if (!diag) {
 #pragma unroll
                 for (int u = 0; u < BPT; ++u) {
 #pragma unroll
@@ -193,7 +253,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
         for (int jj = 0; jj < JC; ++jj) {
             if (j0 + jj < cols) {
 #pragma unroll
-                for (int u = 0; u < BPT; ++u) my_sc[u * K + cst[u][jj]] += acc[u][jj];
+                for (int u = 0; u < BPT; ++u) my_sc[(size_t)u * S3S_THREADS * KP + cst[u][jj]] += acc[u][jj];
             }
         }
     }
@@ -202,7 +262,8 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
     const long long cta_bin0 = (long long)blockIdx.x * BC;
     const long long nvalid = (bins - cta_bin0) < BC ? (bins - cta_bin0) : BC;
     for (long long i = tid; i < nvalid * K; i += S3S_THREADS) {
-        const double v = sc[i];
+        const int lb = (int)(i / K), st = (int)(i - (long long)lb * K);         // local bin = owner thread * BPT + u
+        const double v = sc[((size_t)(lb % BPT) * S3S_THREADS + lb / BPT) * KP + st];
         if (out32 != nullptr) out32[cta_bin0 * K + i] = (float)v;
         if (out64 != nullptr) out64[cta_bin0 * K + i] = v;
     }
@@ -210,13 +271,17 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
 
 template <int BPT, int JC>
 static int launch_s3_score(const uint8_t* xt, int64_t bp, int64_t bins, int cols, int K, const double* terms,
-                           float* o32, double* o64, cudaStream_t st) {
+                           const int* gate, float* o32, double* o64, cudaStream_t st) {
     constexpr int BC = S3S_THREADS * BPT;
     const size_t slab = (size_t)JC * s3_block_stride(K) * 8;
-    const size_t smem = (((size_t)BC * K * 8 + 127) & ~(size_t)127) + 2 * slab + 64;
-    auto kern = s3_score_kernel<BPT, JC>;
-    EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)((bins + BC - 1) / BC), S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, o32, o64);
+    const size_t smem = (((size_t)BC * (K | 1) * 8 + 127) & ~(size_t)127) + 2 * slab + 64;
+    auto sym = s3_score_kernel<BPT, JC, 1>;
+    auto full = s3_score_kernel<BPT, JC, 0>;
+    EPI_CUDA(cudaFuncSetAttribute(sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EPI_CUDA(cudaFuncSetAttribute(full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((bins + BC - 1) / BC);
+    sym<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, o32, o64);
+    full<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, o32, o64);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -261,7 +326,7 @@ extern "C" int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, in
     // choose the blocking that fits 227 KB of shared memory: score rows BC*K*8 + two slabs JC*blk*8
     const size_t blk8 = (size_t)s3_block_stride(K) * 8;
     int bpt = 4, jc = 8;
-    auto fits = [&](int b, int j) { return (size_t)S3S_THREADS * b * K * 8 + 2 * (size_t)j * blk8 + 256 <= 220 * 1024; };
+    auto fits = [&](int b, int j) { return (size_t)S3S_THREADS * b * (K | 1) * 8 + 2 * (size_t)j * blk8 + 256 <= 220 * 1024; };
     if (bins <= S3S_THREADS * 2) bpt = bins <= S3S_THREADS ? 1 : 2;              // small inputs: more CTAs
     while (!fits(bpt, jc) && bpt > 1) bpt >>= 1;
     while (!fits(bpt, jc) && jc > 2) jc >>= 1;
@@ -272,8 +337,16 @@ extern "C" int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, in
     EPI_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xt), (size_t)(bp * cols), st));
     dim3 tg((unsigned)((bp + 63) / 64), (unsigned)((cols + 63) / 64));
     s3_transpose_kernel<<<tg, 256, 0, st>>>(x_dev, bins, cols, pitch, xt, bp);
+    // is the table symmetric (it is whenever it comes from s3Calc)?  decided on the device, no host round trip
+    int* gate = reinterpret_cast<int*>(static_cast<uint8_t*>(device_scratch(nullptr)) + 64 * 8 + 16384 - 64);
+    if (getenv("EPI_S3_FULL") != nullptr) {
+        EPI_CUDA(cudaMemsetAsync(gate, 0, 4, st));                  // A/B runs: force the ordered-pair kernel
+    } else {
+        EPI_CUDA(cudaMemsetAsync(gate, 1, 4, st));
+        s3_symmetry_kernel<<<sm_count() * 8, 256, 0, st>>>(terms_dev, cols, K, gate);
+    }
     int rc = 0;
-#define EPI_S3S_CASE(B, J) if (bpt == B && jc == J) rc = launch_s3_score<B, J>(xt, bp, bins, cols, K, terms_dev, out32_dev, out64_dev, st); else
+#define EPI_S3S_CASE(B, J) if (bpt == B && jc == J) rc = launch_s3_score<B, J>(xt, bp, bins, cols, K, terms_dev, gate, out32_dev, out64_dev, st); else
     EPI_S3S_CASE(4, 8) EPI_S3S_CASE(2, 8) EPI_S3S_CASE(1, 8) EPI_S3S_CASE(4, 4) EPI_S3S_CASE(2, 4) EPI_S3S_CASE(1, 4)
     EPI_S3S_CASE(1, 2) { set_error("no S3 score kernel for blocking %d x %d", bpt, jc); rc = 2; }
 #undef EPI_S3S_CASE

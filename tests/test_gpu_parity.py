@@ -298,6 +298,30 @@ def test_s3_expected_and_scores_match_reference_goldens(eng, golden, name):
     assert np.max(np.abs(s32.cpu().numpy() - g["s3_scores"])) < 2e-2
 
 
+def test_s3_scores_with_a_non_symmetric_expected_table(eng):
+    """The unordered-pair S3 kernel relies on E3[i][j][a][c] == E3[j][i][c][a] (true for every table s3Calc produces) and
+    checks it on the device; a foreign table without that property must take the ordered-pair kernel and still match the
+    restatement.  Also covers a table with zero entries (masked terms) and a j-block that is not full (C = 13)."""
+    rng = np.random.default_rng(5)
+    k, c, bins = 6, 13, 700
+    x = rng.integers(0, k, size=(bins, c)).astype(np.int8)
+    e3 = rng.random((c, c, k, k)).astype(np.float32)
+    e3 /= e3.sum()
+    e3[2, 5] = 0.0                                             # masked terms
+    assert not np.array_equal(e3, e3.transpose(1, 0, 3, 2))
+    xd = dev_states(eng, x)
+    terms = eng.s3_terms(torch.from_numpy(e3).cuda().reshape(-1), c, k)
+    _, s64 = eng.scores_s3(xd, c, k, terms, want64=True)
+    np.testing.assert_allclose(s64.cpu().numpy(), orc.s3_scores_f64(x, k, e3), rtol=RTOL, atol=ATOL)
+    # the symmetrised table takes the unordered-pair kernel: same restatement
+    es = (0.5 * (e3.astype(np.float64) + e3.transpose(1, 0, 3, 2))).astype(np.float32)
+    es = np.maximum(es, es.transpose(1, 0, 3, 2))             # float32 rounding of the two halves made identical
+    assert np.array_equal(es, es.transpose(1, 0, 3, 2))
+    terms = eng.s3_terms(torch.from_numpy(es).cuda().reshape(-1), c, k)
+    _, s64 = eng.scores_s3(xd, c, k, terms, want64=True)
+    np.testing.assert_allclose(s64.cpu().numpy(), orc.s3_scores_f64(x, k, es), rtol=RTOL, atol=ATOL)
+
+
 def test_s3_chunked_accumulation_and_odd_sizes(eng):
     rng = np.random.default_rng(31)
     k, c, bins = 7, 23, 1111                        # CK = 161 -> one 256 block; bins not a multiple of 128
