@@ -35,6 +35,8 @@ CONFIGS = {
     "s2_genome_127": (GENOME_BINS, 127, 15, "S2 whole-genome 15.5M bins x 127 biosamples, 15-state (BASELINE configs[4])"),
     "s1_chr1_833": (1_246_253, 833, 18, "S1 chr1 1,246,253 bins x 833 biosamples, 18-state (shape of BASELINE configs[0])"),
     "s3_chr1_833": (1_250_000, 833, 18, "S3 chr1 1.25M bins x 833 biosamples, 18-state (BASELINE configs[2])"),
+    "paired_s1_chr1": (1_250_000, 833, 18, "paired S1 chr1 1.25M bins, groups of 400 + 433 biosamples, 18-state, 1000 null "
+                                            "permutations per bin (BASELINE configs[3])"),
 }
 
 
@@ -131,6 +133,10 @@ def run_reference(args):
     if rank != 0:
         return
     bins, cols, k, desc = CONFIGS[args.config]
+    if args.config.startswith("paired"):
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the headline S1/S2 configurations only"}),
+              flush=True)
+        return
     saliency = int(args.config[1])
     if saliency == 3:
         print(json.dumps({"impl": "reference", "unavailable": "S3 row-loop port needs ~1 s per bin at 833 biosamples; "
@@ -239,8 +245,10 @@ def run_ours(args):
     bins, cols, k, desc = CONFIGS[args.config]
     if args.bins:
         bins = args.bins
-    saliency = int(args.config[1])
     engine.device_info()
+    if args.config.startswith("paired"):
+        return run_ours_paired(args, engine, synth, dist, world, rank, local, bins, cols, k, desc)
+    saliency = int(args.config[1])
     if saliency == 3:
         return run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, desc)
 
@@ -441,6 +449,76 @@ def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, de
                          "algorithmic_ops_per_launch": useful, "ms_per_launch": gram_ms},
             "e2e": None, "gpu_launches": steps * (2 * ((bins + engine.S3_CHUNK_BINS - 1) // engine.S3_CHUNK_BINS) + 4),
             "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_ours_paired(args, engine, synth, dist, world, rank, local, bins, cols, k, desc):
+    """Paired mode (BASELINE configs[3]): counts of both groups, expected table of the union (all-reduced), scores A / B,
+    delta, quiescence mask, real distances, then P null shuffles per bin (multivariate hypergeometric draws from the group
+    counts, scores of the shuffled groups, signed squared null distance).  The reference draws ONE shuffle per bin;
+    P = 1000 is the north-star configuration.  Parity-test configuration; reported without a roofline fraction (the null
+    stage is bound by the random draws, not by a memory or tensor pipe)."""
+    import torch
+    if args.bins:
+        bins = args.bins
+    c1, c2, nperm, batch = 400, 433, 1000, 20
+    xa = synth.synth_states_device(bins, c1, k, seed=5 + 10 * rank)
+    xb = synth.synth_states_device(bins, c2, k, seed=6 + 10 * rank)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ca = engine.bin_counts(xa, c1, k)
+        cb = engine.bin_counts(xb, c2, k)
+        comb = (ca + cb).contiguous()
+        n1, _ = engine.expected_tables(comb, c1 + c2, want_s2=False)
+        if world > 1:
+            dist.all_reduce(n1)
+        e = engine.normalize(n1)
+        sa, sb = engine.scores_s1(ca, c1, e), engine.scores_s1(cb, c2, e)
+        delta, _ = engine.pairwise_combine(sa, sb, None, None)
+        engine.quiescent_mask(ca, c1, cb, c2, k - 1)
+        engine.pairwise_real_reduce(delta)
+        done = 0
+        while done < nperm:
+            n = min(batch, nperm - done)
+            oa, ob = engine.shuffled_counts_philox(ca, cb, c1, c2, 100 + done, n)
+            na = engine.scores_s1(oa.reshape(-1, k), c1, e)
+            nb = engine.scores_s1(ob.reshape(-1, k), c2, e)
+            engine.pairwise_combine(None, None, na, nb)
+            done += n
+
+    steps = min(args.steps, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if sampler:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(steps):
+        step()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_per_step = float(ms[0])
+        line = {
+            "metric": "bins/sec for paired expected+scores (S1) with %d null permutations per bin" % nperm,
+            "value": bins * world / (ms_per_step * 1e-3), "unit": "bins/s", "n_gpus": world, "steps": steps, "warmup": 1,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64+f64", "data": "synthetic",
+            "config": {"workload": desc, "bins_per_gpu": bins, "group_sizes": [c1, c2], "states": k, "saliency": 1,
+                       "null_permutations": nperm, "bin_permutation_pairs_per_s": bins * world * nperm / (ms_per_step * 1e-3)},
+            "roofline": None, "e2e": None, "gpu_launches": steps * (12 + (nperm // batch) * 6), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
