@@ -346,7 +346,8 @@ template <int BV, int MODE>
 static int launch_k1(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, int num_states, uint16_t* cnt,
                           cudaStream_t stream) {
     constexpr int stage_bytes = BV * 16 * K1_ROWS;
-    int stages = (BV <= 3) ? 8 : 3;           // measured on B200 at 833 biosamples: 3 stages x 2 CTAs/SM is best
+    int stages = (BV <= 3) ? 8 : (BV <= 9 ? 4 : 3);           // measured on B200 at 833 biosamples (tools/k1_sweep.py): 4 stages x 2 CTAs/SM: 2.22 ms;
+                                              // 3 x 2: 2.26, 5 x 2: 2.26, 3 x 3: 2.32, 2 x 4: 2.35, 6 x 1: 2.79
     int ctas_per_sm = (BV <= 3) ? 3 : 2;
     if (const char* e = getenv("EPI_K1_STAGES")) stages = atoi(e) > 0 ? atoi(e) : stages;      // tuning knobs
     if (const char* e = getenv("EPI_K1_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;
