@@ -46,18 +46,19 @@ def pitch_for(cols):
     return (int(cols) + 15) & ~15
 
 
-def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=False):
+def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=False, shape=None):
     """Parse one input matrix file: `chr start end state_1 ... state_C` (README.md:286-292).
 
     Returns (locations, states0): states0 is an int8 [rows, C] view (row pitch = multiple of 16 bytes, i.e. already
     in the kernels' layout; `states0.base` is the pitched buffer) holding label-1 (helpers.py:154-155); locations
     is None or dict(chrom=object array, start=int64 array, end=int64 array).
     `rows` = (lo, hi) restricts the parse to that row range (skiprows / nrows of helpers.py:154-155).
-    Labels outside 1..num_states raise (the reference would fail later with an IndexError)."""
+    Labels outside 1..num_states raise (the reference would fail later with an IndexError).
+    `shape` = (total rows, biosample columns) if the caller already knows them (saves one inflate pass over the file)."""
     path = Path(path)
     if not path.is_file():
         raise FileNotFoundError(str(path))
-    total, cols = tsv_shape(path)
+    total, cols = tsv_shape(path) if shape is None else shape
     if cols < 1:
         raise ValueError("%s: expected `chr start end state_1 ...` rows" % path)
     lo, hi = (0, total) if rows is None else (int(rows[0]), int(rows[1]))

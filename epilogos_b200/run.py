@@ -201,6 +201,8 @@ def main(mode, commandLineBool, inputDirectory, inputDirectory1, inputDirectory2
                                         + "directories 1 and 2 have the same name")
             pairs.append((f, match))
 
+    from . import session
+    session.prefetch(pairs, numStates)                   # parse all files concurrently, once (the stages re-use them)
     say("\nSTEP 1: Per data file background frequency calculation")
     for f, f2 in pairs:
         expected.main(f, f2, numStates, saliency, outputDirPath, fileTag, numProcesses, verbose)

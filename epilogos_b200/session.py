@@ -27,15 +27,19 @@ def get_backend(backend=None):
 class Shard:
     """The rows [lo, hi) of one input file (or file pair) owned by this rank."""
 
-    def __init__(self, file1, file2, num_states, backend):
+    def __init__(self, file1, file2, num_states, backend, rank=0, world=0):
         self.backend = get_backend(backend)
         self.num_states = num_states
-        self.total_rows = helpers.countRows(file1)
-        self.lo, self.hi = helpers.splitRows(self.total_rows, dist.world_size())[dist.rank()]
+        if not Path(file1).is_file():
+            raise FileNotFoundError(str(file1))
+        shape = helpers.tsv_shape(file1)                 # one inflate pass: newline count + columns; reused by the parse
+        self.total_rows = shape[0]
+        self.lo, self.hi = helpers.splitRows(self.total_rows, world if world else dist.world_size())[
+            rank if world else dist.rank()]
         rows = (self.lo, self.hi)
         pinned = getattr(self.backend, "name", "") == "cuda"
         self.loc, self.states_a = helpers.read_matrix(file1, rows, want_locations=True, num_states=num_states,
-                                                      pinned=pinned)
+                                                      pinned=pinned, shape=shape)
         self.states_b = None
         if str(file2) != "null":
             _, self.states_b = helpers.read_matrix(file2, rows, want_locations=False, num_states=num_states)
@@ -79,13 +83,39 @@ def _key(file1, file2):
     return (str(p1), st.st_mtime_ns, st.st_size, str(file2), dist.rank(), dist.world_size())
 
 
-def load_shard(file1, file2, num_states, backend=None, keep=4):
+_keep = 4
+
+
+def load_shard(file1, file2, num_states, backend=None, keep=None):
     key = _key(file1, file2)
     if key not in _cache:
-        while len(_cache) >= keep:
+        while len(_cache) >= (keep or _keep):
             _cache.pop(next(iter(_cache)))
         _cache[key] = Shard(file1, file2, num_states, backend)
     return _cache[key]
+
+
+def prefetch(pairs, num_states, backend=None, workers=None):
+    """Parse this rank's rows of ALL input files concurrently, before the stages run.  The reference parses every file
+    again in every stage and worker; the native packer (csrc/hostio.cu) releases the GIL and uses two threads per file
+    (inflate | parse), so a whole-genome directory of per-chromosome files is read in the time of its largest files
+    instead of their sum.  The cache is sized to hold every file, so the score stage re-uses the parsed matrices and the
+    device-resident counts of the expected stage."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    global _keep
+    pairs = list(pairs)
+    _keep = max(_keep, len(pairs) + 1)
+    todo = [(f, f2) for f, f2 in pairs if _key(f, f2) not in _cache]
+    if not todo:
+        return
+    be = get_backend(backend)
+    rank, world = dist.rank(), dist.world_size()          # resolved on the calling thread
+    workers = workers or max(1, min(len(todo), (os.cpu_count() or 2) // 2))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        shards = list(pool.map(lambda p: Shard(p[0], p[1], num_states, be, rank=rank, world=world), todo))
+    for (f, f2), sh in zip(todo, shards):
+        _cache[_key(f, f2)] = sh
 
 
 def clear():

@@ -75,6 +75,44 @@ def test_single_pipeline_files_match_reference(tmp_path, golden, saliency):
     assert text == g["s%d_text" % saliency].tobytes()
 
 
+def test_prefetch_parses_every_file_once_and_stages_reuse_it(tmp_path, golden, monkeypatch):
+    """session.prefetch (what the CLI calls before STEP 1): all files of a directory are parsed concurrently, once; the
+    expected and the score stage of every file find their shard in the cache (no second parse), and the multi-file
+    table equals the table of the concatenated matrix (expectedCombination.py:30-35)."""
+    from fake_backend import OracleBackend
+    from epilogos_b200 import expected, expectedCombination, helpers, scores, session
+    from oracle import epilogos_oracle as orc
+    session.clear()
+    x = golden("real10_chr1_k18")["x"]
+    parts = [x[:700], x[700:1500], x[1500:2100], x[2100:2600], x[2600:3000], x[3000:3300]]
+    inp = tmp_path / "in"; out = tmp_path / "out"
+    inp.mkdir(); out.mkdir()
+    files = []
+    for i, part in enumerate(parts):
+        f = inp / ("epilogos_matrix_chr%d.txt.gz" % (i + 1))
+        write_tsv(f, part, chrom="chr%d" % (i + 1), gz=True)
+        files.append(f)
+    be = OracleBackend()
+    calls = []
+    real = helpers.read_matrix
+    monkeypatch.setattr(helpers, "read_matrix", lambda *a, **k: (calls.append(str(a[0])), real(*a, **k))[1])
+    session.prefetch([(f, "null") for f in files], 18, backend=be, workers=3)
+    assert sorted(calls) == sorted(str(f) for f in files)
+    for f in files:
+        expected.main(f, "null", 18, 2, out, "t", 1, False, backend=be)
+    exp_path = out / "exp_freq_t.npy"
+    expectedCombination.main(out, exp_path, "t", False, backend=be)
+    for f in files:
+        scores.main(f, "null", 18, 2, out, exp_path, "t", 1, 17, -1, False, backend=be)
+    assert len(calls) == len(files)                                   # nothing was parsed twice
+    whole = np.concatenate(parts)
+    assert np.load(exp_path).tobytes() == orc.normalize_expected(orc.s2_expected_counts(whole, 18)).tobytes()
+    got = np.concatenate([np.load(out / ("temp_scores_t_epilogos_matrix_chr%d.npz" % (i + 1)), allow_pickle=True)["scoreArr"]
+                          for i in range(len(parts))])
+    assert got.tobytes() == orc.s2_scores(whole, 18, np.load(exp_path)).tobytes()
+    session.clear()
+
+
 def test_bad_saliency_raises(tmp_path):
     from fake_backend import OracleBackend
     from epilogos_b200 import expected
