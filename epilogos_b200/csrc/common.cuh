@@ -69,6 +69,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Release of a shared-memory buffer to an asynchronous producer (TMA / bulk copy): the arrive must not be performed before
+// the loads that read the buffer have returned.  An arrive issued right behind the loads can overtake them (measured in
+// tc_tables.cu: corrupted rows), so these variants take a value that DEPENDS on the loaded data as an (unused) operand:
+// the instruction cannot issue until that value exists, i.e. until the loads have completed.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, double dep) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "d"(dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

@@ -242,7 +242,8 @@ k1_counts_kernel(const __grid_constant__ CUtensorMap tmap, long long bins, int n
             const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)s * STAGE_BYTES + tid * (BV * 16));
             process_chunk<BV, MODE, NP>(row, p, sum1, sum2, one);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            // p[0] is the XOR of every one-hot word of the chunk: it exists only after all of the chunk's loads returned
+            if (lane == 0) mbar_arrive_after(&empty[s], p[0]);
             if (++s == stages) {
                 s = 0;
                 ph ^= 1;

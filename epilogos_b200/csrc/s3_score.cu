@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) s3_symmetry_kernel(const double* __restri
 template <int BPT, int JC, int SYM>
 __global__ void __launch_bounds__(S3S_THREADS + 32, 1)
 s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, int cols, int K,
-                const double* __restrict__ terms, const int* __restrict__ gate, float* __restrict__ out32,
+                const double* __restrict__ terms, const int* __restrict__ gate, int nslab, float* __restrict__ out32,
                 double* __restrict__ out64) {
     if ((*gate != 0) != (SYM != 0)) return;
     constexpr int BC = S3S_THREADS * BPT;
@@ -111,14 +111,14 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
     // update the same state (the SYM kernel read-modify-writes one row entry per bin and slab)
     const int KP = K | 1;
     double* sc = reinterpret_cast<double*>(smem);                                   // [BPT][256][KP]
-    uint8_t* slabs = smem + (((size_t)BC * KP * 8 + 127) & ~(size_t)127);          // 2 slabs
-    uint64_t* full = reinterpret_cast<uint64_t*>(slabs + 2 * (size_t)slab_bytes);
-    uint64_t* empty = full + 2;
+    uint8_t* slabs = smem + (((size_t)BC * KP * 8 + 127) & ~(size_t)127);          // nslab slabs
+    uint64_t* full = reinterpret_cast<uint64_t*>(slabs + (size_t)nslab * slab_bytes);
+    uint64_t* empty = full + nslab;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < nslab; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], S3S_THREADS / 32);
         }
@@ -140,7 +140,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
                     mbar_expect_tx(&full[s], slab_bytes);
                     bulk_load_1d(slabs + (size_t)s * slab_bytes, terms + ((long long)i * cols + jb * JC) * blk,
                                  slab_bytes, &full[s]);
-                    if (++s == 2) {
+                    if (++s == nslab) {
                         s = 0;
                         ph ^= 1;
                     }
@@ -202,6 +202,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
             mbar_wait(&full[s], ph);
             const uint32_t base = slab0 + (uint32_t)s * (uint32_t)slab_bytes;
             const bool diag = (i >= j0) && (i < j0 + JC);
+            double dep = 0.0;                                    // the last value read from the slab (see mbar_arrive_after)
             if (SYM) {
                 // unordered pairs i < j: the term goes to the bucket of x_j (registers) and to the bucket of x_i (score row)
 #pragma unroll
@@ -214,6 +215,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
                             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
                             acc[u][jj] += t;
                             si += t;
+                            dep = t;
                         }
                     }
                     my_sc[(size_t)u * S3S_THREADS * KP + ai[u]] += si;
@@ -226,6 +228,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
                         double t;
                         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
                         acc[u][jj] += t;
+                        dep = t;
                     }
                 }
             } else {
@@ -237,13 +240,20 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
                             double t;
                             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(base + a[u] + off[u][jj]));
                             acc[u][jj] += t;
+                            dep = t;
                         }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == 2) {
+            // The slab goes back to the producer only after its look-ups have returned.  SYM: the read-modify-write of the
+            // score row above depends on every loaded term and precedes the arrive in program order.  Ordered-pair kernel:
+            // the arrive takes the last loaded value as an operand (mbar_arrive_after, common.cuh).
+            if (lane == 0) {
+                if (SYM) mbar_arrive(&empty[s]);
+                else mbar_arrive_after(&empty[s], dep);
+            }
+            if (++s == nslab) {
                 s = 0;
                 ph ^= 1;
             }
@@ -274,14 +284,16 @@ static int launch_s3_score(const uint8_t* xt, int64_t bp, int64_t bins, int cols
                            const int* gate, float* o32, double* o64, cudaStream_t st) {
     constexpr int BC = S3S_THREADS * BPT;
     const size_t slab = (size_t)JC * s3_block_stride(K) * 8;
-    const size_t smem = (((size_t)BC * (K | 1) * 8 + 127) & ~(size_t)127) + 2 * slab + 64;
+    const size_t rows = (((size_t)BC * (K | 1) * 8 + 127) & ~(size_t)127);
+    const int nslab = rows + 4 * slab + 128 <= 224 * 1024 ? 4 : (rows + 3 * slab + 128 <= 224 * 1024 ? 3 : 2);
+    const size_t smem = rows + (size_t)nslab * slab + 128;
     auto sym = s3_score_kernel<BPT, JC, 1>;
     auto full = s3_score_kernel<BPT, JC, 0>;
     EPI_CUDA(cudaFuncSetAttribute(sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EPI_CUDA(cudaFuncSetAttribute(full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((bins + BC - 1) / BC);
-    sym<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, o32, o64);
-    full<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, o32, o64);
+    sym<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, nslab, o32, o64);
+    full<<<grid, S3S_THREADS + 32, smem, st>>>(xt, bp, bins, cols, K, terms, gate, nslab, o32, o64);
     EPI_CUDA(cudaGetLastError());
     return 0;
 }
