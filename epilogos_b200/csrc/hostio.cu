@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -236,6 +237,79 @@ struct LineSource {
     }
 };
 
+// One row `chr \t start \t end \t s_1 .. s_C` -> labels-1 in dst[0..cols), coordinates, chromosome id (names grows).
+// Returns 0, or 2 with the error set.
+static int parse_row(const char* path, int64_t row, const char* p, const char* e, int32_t cols, int32_t num_states,
+                     int8_t* dst, int64_t* start, int64_t* end, int32_t* chrom, std::vector<std::string>& names,
+                     int& last_id, bool want_chrom) {
+    if (e > p && e[-1] == '\r') --e;
+    // ---- chromosome name ----
+    const char* t = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
+    EPI_REQUIRE(t != nullptr, "%s: row %lld is truncated (expected chr<TAB>start<TAB>end<TAB>states)", path,
+                (long long)row);
+    if (want_chrom) {
+        const size_t nl = (size_t)(t - p);
+        int id = -1;
+        if (last_id >= 0 && names[last_id].size() == nl && memcmp(names[last_id].data(), p, nl) == 0) id = last_id;
+        for (size_t i = 0; id < 0 && i < names.size(); ++i)
+            if (names[i].size() == nl && memcmp(names[i].data(), p, nl) == 0) id = (int)i;
+        if (id < 0) {
+            id = (int)names.size();
+            names.emplace_back(p, nl);
+        }
+        *chrom = last_id = id;
+    }
+    p = t + 1;
+    // ---- start, end ----
+    for (int f = 0; f < 2; ++f) {
+        long long v = 0;
+        bool negv = false;
+        if (p < e && *p == '-') {
+            negv = true;
+            ++p;
+        }
+        const char* d0 = p;
+        while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+        EPI_REQUIRE(p > d0 && p < e && *p == '\t', "%s: row %lld: bad coordinate field", path, (long long)row);
+        ++p;
+        if (f == 0 && start) *start = negv ? -v : v;
+        if (f == 1 && end) *end = negv ? -v : v;
+    }
+    // ---- state labels: 1..num_states, one to three digits ----
+    int j = 0;
+    while (j < cols) {
+        EPI_REQUIRE(p < e, "%s: row %lld has %d state columns, expected %d", path, (long long)row, j, cols);
+        unsigned v = (unsigned)(*p - '0');
+        EPI_REQUIRE(v <= 9, "%s: row %lld column %d: state label is not an integer", path, (long long)row, j + 4);
+        ++p;
+        while (p < e && (unsigned)(*p - '0') <= 9) {
+            v = v * 10 + (unsigned)(*p++ - '0');
+            EPI_REQUIRE(v <= 1000, "%s: row %lld column %d: state label out of range", path, (long long)row, j + 4);
+        }
+        EPI_REQUIRE(v >= 1 && v <= (unsigned)num_states, "%s: row %lld column %d: state %u outside 1..%d", path,
+                    (long long)row, j + 4, v, num_states);
+        dst[j++] = (int8_t)(v - 1);
+        if (p < e) {
+            EPI_REQUIRE(*p == '\t', "%s: row %lld column %d: unexpected character", path, (long long)row, j + 3);
+            ++p;
+            EPI_REQUIRE(j < cols || p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
+        }
+    }
+    EPI_REQUIRE(p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
+    return 0;
+}
+
+static int emit_names(const std::vector<std::string>& names, char* chrom_names, int32_t chrom_names_cap) {
+    if (chrom_names == nullptr) return 0;
+    size_t off = 0;
+    for (const std::string& s : names) {
+        EPI_REQUIRE(off + s.size() + 1 <= (size_t)chrom_names_cap, "chromosome name buffer too small");
+        memcpy(chrom_names + off, s.c_str(), s.size() + 1);
+        off += s.size() + 1;
+    }
+    return 0;
+}
+
 extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states,
                             int8_t* out, int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id,
                             char* chrom_names, int32_t chrom_names_cap, int32_t* n_chrom_out) {
@@ -255,73 +329,94 @@ extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, in
     for (; row < row_hi; ++row) {
         EPI_REQUIRE(src.next_line(p, e, has_nl), "%s ends after %lld rows, wanted rows up to %lld", path, (long long)row,
                     (long long)row_hi);
-        if (e > p && e[-1] == '\r') --e;
         const int64_t r = row - row_lo;
-        // ---- chromosome name ----
-        const char* t = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
-        EPI_REQUIRE(t != nullptr, "%s: row %lld is truncated (expected chr<TAB>start<TAB>end<TAB>states)", path,
-                    (long long)row);
-        if (chrom_id != nullptr) {
-            const size_t nl = (size_t)(t - p);
-            int id = -1;
-            if (last_id >= 0 && names[last_id].size() == nl && memcmp(names[last_id].data(), p, nl) == 0) id = last_id;
-            for (size_t i = 0; id < 0 && i < names.size(); ++i)
-                if (names[i].size() == nl && memcmp(names[i].data(), p, nl) == 0) id = (int)i;
-            if (id < 0) {
-                id = (int)names.size();
-                names.emplace_back(p, nl);
-            }
-            chrom_id[r] = last_id = id;
-        }
-        p = t + 1;
-        // ---- start, end ----
-        for (int f = 0; f < 2; ++f) {
-            long long v = 0;
-            bool negv = false;
-            if (p < e && *p == '-') {
-                negv = true;
-                ++p;
-            }
-            const char* d0 = p;
-            while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
-            EPI_REQUIRE(p > d0 && p < e && *p == '\t', "%s: row %lld: bad coordinate field", path, (long long)row);
-            ++p;
-            if (f == 0 && starts) starts[r] = negv ? -v : v;
-            if (f == 1 && ends) ends[r] = negv ? -v : v;
-        }
-        // ---- state labels: 1..num_states, one to three digits ----
         int8_t* dst = out + r * pitch;
-        int j = 0;
-        while (j < cols) {
-            EPI_REQUIRE(p < e, "%s: row %lld has %d state columns, expected %d", path, (long long)row, j, cols);
-            unsigned v = (unsigned)(*p - '0');
-            EPI_REQUIRE(v <= 9, "%s: row %lld column %d: state label is not an integer", path, (long long)row, j + 4);
-            ++p;
-            while (p < e && (unsigned)(*p - '0') <= 9) {
-                v = v * 10 + (unsigned)(*p++ - '0');
-                EPI_REQUIRE(v <= 1000, "%s: row %lld column %d: state label out of range", path, (long long)row, j + 4);
-            }
-            EPI_REQUIRE(v >= 1 && v <= (unsigned)num_states, "%s: row %lld column %d: state %u outside 1..%d", path,
-                        (long long)row, j + 4, v, num_states);
-            dst[j++] = (int8_t)(v - 1);
-            if (p < e) {
-                EPI_REQUIRE(*p == '\t', "%s: row %lld column %d: unexpected character", path, (long long)row, j + 3);
-                ++p;
-                EPI_REQUIRE(j < cols || p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
-            }
-        }
-        EPI_REQUIRE(p == e, "%s: row %lld has more than %d state columns", path, (long long)row, cols);
+        int32_t cid = 0;
+        if (int rc = parse_row(path, row, p, e, cols, num_states, dst, starts ? starts + r : nullptr,
+                               ends ? ends + r : nullptr, &cid, names, last_id, chrom_id != nullptr))
+            return rc;
+        if (chrom_id != nullptr) chrom_id[r] = cid;
         for (int64_t jj = cols; jj < pitch; ++jj) dst[jj] = 0;
     }
     if (n_chrom_out) *n_chrom_out = (int32_t)names.size();
-    if (chrom_names != nullptr) {
-        size_t off = 0;
-        for (const std::string& s : names) {
-            EPI_REQUIRE(off + s.size() + 1 <= (size_t)chrom_names_cap, "chromosome name buffer too small");
-            memcpy(chrom_names + off, s.c_str(), s.size() + 1);
-            off += s.size() + 1;
+    return emit_names(names, chrom_names, chrom_names_cap);
+}
+
+// ---- single-pass parse of a whole file: the row count need not be known beforehand (saves the newline-count pass,
+//      i.e. one of two inflate passes, which is what bounds reading a gzipped matrix) ------------------------------
+namespace epi {
+struct ParsedFile {
+    static constexpr int64_t CHUNK_ROWS = 1 << 15;
+    int32_t cols = 0;
+    int64_t rows = 0;
+    std::vector<std::vector<int8_t>> labels;      // chunks of CHUNK_ROWS x cols
+    std::vector<int64_t> starts, ends;
+    std::vector<int32_t> chrom;
+    std::vector<std::string> names;
+};
+}  // namespace epi
+
+extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out,
+                                  int32_t* cols_out, int32_t* n_chrom_out, int32_t* names_bytes_out) {
+    EPI_REQUIRE(path != nullptr && handle_out != nullptr, "null pointer argument");
+    EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
+    LineSource src;
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    std::unique_ptr<ParsedFile> pf(new ParsedFile());
+    const char *p, *e;
+    bool has_nl;
+    int last_id = -1;
+    while (src.next_line(p, e, has_nl)) {
+        if (!has_nl) break;                           // rows = newline count (helpers.countRows): an unterminated tail is not a row
+        if (pf->rows == 0) {
+            int tabs = 0;
+            for (const char* q = p; q < e; ++q) tabs += (*q == '\t');
+            pf->cols = tabs + 1 - 3;
+            EPI_REQUIRE(pf->cols >= 1, "%s: expected `chr start end state_1 ...` rows", path);
         }
+        const int64_t r = pf->rows;
+        if (r % ParsedFile::CHUNK_ROWS == 0) pf->labels.emplace_back((size_t)ParsedFile::CHUNK_ROWS * pf->cols);
+        int8_t* dst = pf->labels.back().data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+        int64_t st = 0, en = 0;
+        int32_t cid = 0;
+        if (int rc = parse_row(path, r, p, e, pf->cols, num_states, dst, &st, &en, &cid, pf->names, last_id, true)) return rc;
+        pf->starts.push_back(st);
+        pf->ends.push_back(en);
+        pf->chrom.push_back(cid);
+        ++pf->rows;
     }
+    size_t nb = 0;
+    for (const std::string& s : pf->names) nb += s.size() + 1;
+    if (rows_out) *rows_out = pf->rows;
+    if (cols_out) *cols_out = pf->cols;
+    if (n_chrom_out) *n_chrom_out = (int32_t)pf->names.size();
+    if (names_bytes_out) *names_bytes_out = (int32_t)nb;
+    *handle_out = pf.release();
+    return 0;
+}
+
+extern "C" int epi_tsv_parse_fetch(void* handle, int64_t row_lo, int64_t row_hi, int8_t* out, int64_t pitch, int64_t* starts,
+                                   int64_t* ends, int32_t* chrom_id, char* chrom_names, int32_t chrom_names_cap) {
+    ParsedFile* pf = static_cast<ParsedFile*>(handle);
+    EPI_REQUIRE(pf != nullptr, "null handle");
+    EPI_REQUIRE(row_lo >= 0 && row_hi >= row_lo && row_hi <= pf->rows, "row range [%lld, %lld) outside the %lld parsed rows",
+                (long long)row_lo, (long long)row_hi, (long long)pf->rows);
+    EPI_REQUIRE(row_hi == row_lo || (out != nullptr && pitch >= pf->cols), "bad output buffer");
+    for (int64_t r = row_lo; r < row_hi; ++r) {
+        const int8_t* src = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+        int8_t* dst = out + (r - row_lo) * pitch;
+        memcpy(dst, src, (size_t)pf->cols);
+        if (pitch > pf->cols) memset(dst + pf->cols, 0, (size_t)(pitch - pf->cols));
+    }
+    const size_t n = (size_t)(row_hi - row_lo);
+    if (starts && n) memcpy(starts, pf->starts.data() + row_lo, n * sizeof(int64_t));
+    if (ends && n) memcpy(ends, pf->ends.data() + row_lo, n * sizeof(int64_t));
+    if (chrom_id && n) memcpy(chrom_id, pf->chrom.data() + row_lo, n * sizeof(int32_t));
+    return emit_names(pf->names, chrom_names, chrom_names_cap);
+}
+
+extern "C" int epi_tsv_parse_close(void* handle) {
+    delete static_cast<ParsedFile*>(handle);
     return 0;
 }
 

@@ -46,47 +46,82 @@ def pitch_for(cols):
     return (int(cols) + 15) & ~15
 
 
-def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=False, shape=None):
+def _alloc_rows(n, pitch, pinned):
+    if pinned:
+        import torch
+        return torch.empty((n, pitch), dtype=torch.int8, pin_memory=True).numpy()     # the view keeps the pinned storage alive
+    return np.empty((n, pitch), dtype=np.int8)
+
+
+def _locations(names_raw, n_names, cid, starts, ends, n):
+    uniq = names_raw.split(b"\0")[:n_names]
+    table = np.array([u.decode() for u in uniq], dtype=object) if uniq else np.array([], dtype=object)
+    return dict(chrom=table[cid] if n else np.array([], dtype=object), start=starts, end=ends,
+                chrom_id=cid, chrom_names=b"\0".join(uniq) + b"\0")
+
+
+def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=False, shape=None, split=None,
+                return_total=False):
     """Parse one input matrix file: `chr start end state_1 ... state_C` (README.md:286-292).
 
     Returns (locations, states0): states0 is an int8 [rows, C] view (row pitch = multiple of 16 bytes, i.e. already
     in the kernels' layout; `states0.base` is the pitched buffer) holding label-1 (helpers.py:154-155); locations
     is None or dict(chrom=object array, start=int64 array, end=int64 array).
-    `rows` = (lo, hi) restricts the parse to that row range (skiprows / nrows of helpers.py:154-155).
+    `rows` = (lo, hi) restricts the parse to that row range (skiprows / nrows of helpers.py:154-155); `split` = (rank,
+    world) selects this rank's range splitRows(total, world)[rank] instead, without knowing `total` beforehand.
     Labels outside 1..num_states raise (the reference would fail later with an IndexError).
-    `shape` = (total rows, biosample columns) if the caller already knows them (saves one inflate pass over the file)."""
+    With `rows` and `shape` = (total rows, biosample columns) the file is read by the two-call packer (epi_pack_tsv);
+    otherwise it is parsed in ONE pass (epi_tsv_parse_*: the row count comes out of the parse), which saves one of the
+    two inflate passes that bound reading a gzipped matrix.  `return_total` appends the file's total row count."""
     path = Path(path)
     if not path.is_file():
         raise FileNotFoundError(str(path))
-    total, cols = tsv_shape(path) if shape is None else shape
-    if cols < 1:
-        raise ValueError("%s: expected `chr start end state_1 ...` rows" % path)
-    lo, hi = (0, total) if rows is None else (int(rows[0]), int(rows[1]))
-    n = max(hi - lo, 0)
-    pitch = pitch_for(cols)
-    if pinned:
-        import torch
-        holder = torch.empty((n, pitch), dtype=torch.int8, pin_memory=True)
-        buf = holder.numpy()
+    if rows is not None and shape is not None:
+        total, cols = shape
+        lo, hi = int(rows[0]), int(rows[1])
+        n = max(hi - lo, 0)
+        pitch = pitch_for(cols)
+        buf = _alloc_rows(n, pitch, pinned)
+        starts = np.empty(n, dtype=np.int64)
+        ends = np.empty(n, dtype=np.int64)
+        cid = np.empty(n, dtype=np.int32)
+        names = ctypes.create_string_buffer(1 << 16)
+        nnames = ctypes.c_int32(0)
+        _lib.call("epi_pack_tsv", str(path).encode(), lo, hi, cols, int(num_states), ctypes.c_void_p(buf.ctypes.data),
+                  pitch, ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
+                  ctypes.c_void_p(cid.ctypes.data), names, len(names), ctypes.byref(nnames))
+        names_raw, n_names = names.raw, nnames.value
     else:
-        holder = None
-        buf = np.empty((n, pitch), dtype=np.int8)
-    starts = np.empty(n, dtype=np.int64)
-    ends = np.empty(n, dtype=np.int64)
-    cid = np.empty(n, dtype=np.int32)
-    names = ctypes.create_string_buffer(1 << 16)
-    nnames = ctypes.c_int32(0)
-    _lib.call("epi_pack_tsv", str(path).encode(), lo, hi, cols, int(num_states), ctypes.c_void_p(buf.ctypes.data),
-              pitch, ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
-              ctypes.c_void_p(cid.ctypes.data), names, len(names), ctypes.byref(nnames))
-    states0 = buf[:, :cols]
-    loc = None
-    if want_locations:
-        uniq = names.raw.split(b"\0")[: nnames.value]
-        table = np.array([u.decode() for u in uniq], dtype=object) if uniq else np.array([], dtype=object)
-        loc = dict(chrom=table[cid] if n else np.array([], dtype=object), start=starts, end=ends,
-                   chrom_id=cid, chrom_names=b"\0".join(uniq) + b"\0")
-    return loc, states0          # states0 (a numpy view) keeps the pinned torch storage alive
+        handle = ctypes.c_void_p(0)
+        total_c, cols_c = ctypes.c_int64(0), ctypes.c_int32(0)
+        nnames, nbytes = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.call("epi_tsv_parse_open", str(path).encode(), int(num_states), ctypes.byref(handle), ctypes.byref(total_c),
+                  ctypes.byref(cols_c), ctypes.byref(nnames), ctypes.byref(nbytes))
+        try:
+            total, cols = total_c.value, cols_c.value
+            if total > 0 and cols < 1:
+                raise ValueError("%s: expected `chr start end state_1 ...` rows" % path)
+            if split is not None:
+                rows = splitRows(total, int(split[1]))[int(split[0])]
+            lo, hi = (0, total) if rows is None else (int(rows[0]), int(rows[1]))
+            n = max(hi - lo, 0)
+            pitch = pitch_for(max(cols, 1))
+            buf = _alloc_rows(n, pitch, pinned)
+            starts = np.empty(n, dtype=np.int64)
+            ends = np.empty(n, dtype=np.int64)
+            cid = np.empty(n, dtype=np.int32)
+            names = ctypes.create_string_buffer(max(nbytes.value, 1))
+            _lib.call("epi_tsv_parse_fetch", handle, lo, hi, ctypes.c_void_p(buf.ctypes.data), pitch,
+                      ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
+                      ctypes.c_void_p(cid.ctypes.data), names, len(names))
+            names_raw, n_names = names.raw, nnames.value
+        finally:
+            _lib.call("epi_tsv_parse_close", handle)
+    states0 = buf[:, :max(cols, 0)]
+    loc = _locations(names_raw, n_names, cid, starts, ends, n) if want_locations else None
+    if return_total:
+        return loc, states0, total
+    return loc, states0
 
 
 def sharedToNumpy(sharedArr, numRows, numStates):

@@ -32,14 +32,14 @@ class Shard:
         self.num_states = num_states
         if not Path(file1).is_file():
             raise FileNotFoundError(str(file1))
-        shape = helpers.tsv_shape(file1)                 # one inflate pass: newline count + columns; reused by the parse
-        self.total_rows = shape[0]
-        self.lo, self.hi = helpers.splitRows(self.total_rows, world if world else dist.world_size())[
-            rank if world else dist.rank()]
-        rows = (self.lo, self.hi)
+        # one pass over the file: the row count comes out of the parse, this rank's range is cut from the parsed rows
         pinned = getattr(self.backend, "name", "") == "cuda"
-        self.loc, self.states_a = helpers.read_matrix(file1, rows, want_locations=True, num_states=num_states,
-                                                      pinned=pinned, shape=shape)
+        split = (rank, world) if world else (dist.rank(), dist.world_size())
+        self.loc, self.states_a, self.total_rows = helpers.read_matrix(file1, None, want_locations=True,
+                                                                       num_states=num_states, pinned=pinned,
+                                                                       split=split, return_total=True)
+        self.lo, self.hi = helpers.splitRows(self.total_rows, split[1])[split[0]]
+        rows = (self.lo, self.hi)
         self.states_b = None
         if str(file2) != "null":
             _, self.states_b = helpers.read_matrix(file2, rows, want_locations=False, num_states=num_states)

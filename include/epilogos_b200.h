@@ -166,8 +166,17 @@ int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pi
  *                     names as consecutive NUL-terminated strings.  Replaces the pandas parse of helpers.readStates
  *                     (helpers.py:150-168) and of scores.py:161.  Labels outside 1..num_states are an error.
  * epi_write_scores_gz `chr\tstart\tend\t` + K x "%.5f" per row through gzip (scores.writeScores, scores.py:509-536);
- *                     decompressed text is byte-identical to the reference's.  level 0-9 (else 6), threads <= 0 = all. */
+ *                     decompressed text is byte-identical to the reference's.  level 0-9 (else 6), threads <= 0 = all.
+ * epi_tsv_parse_*     the same parse in ONE pass over the file when the row count is not known beforehand (inflating a
+ *                     gzipped matrix is what bounds reading it): _open parses the whole file into a library-owned
+ *                     staging area and reports rows / columns / chromosome names; _fetch copies a row range into the
+ *                     caller's (pinned) buffers exactly as epi_pack_tsv would have written them; _close frees it. */
 int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
+int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out, int32_t* cols_out,
+                       int32_t* n_chrom_out, int32_t* names_bytes_out);
+int epi_tsv_parse_fetch(void* handle, int64_t row_lo, int64_t row_hi, int8_t* out, int64_t pitch, int64_t* starts,
+                        int64_t* ends, int32_t* chrom_id, char* chrom_names, int32_t chrom_names_cap);
+int epi_tsv_parse_close(void* handle);
 int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states, int8_t* out,
                  int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id, char* chrom_names,
                  int32_t chrom_names_cap, int32_t* n_chrom_out);

@@ -69,8 +69,41 @@ def test_packer_shapes_ranges_and_validation(tmp_path):
             helpers.read_matrix(b, num_states=18)
     with pytest.raises(FileNotFoundError):
         helpers.read_matrix(tmp_path / "missing.txt")
+    with pytest.raises(EpilogosB200Error, match="outside the 10 parsed rows"):
+        helpers.read_matrix(f, rows=(20, 30), num_states=18)                       # one-pass parser
     with pytest.raises(EpilogosB200Error, match="only"):
-        helpers.read_matrix(f, rows=(20, 30), num_states=18)
+        helpers.read_matrix(f, rows=(20, 30), num_states=18, shape=(10, 3))       # two-call packer
+
+
+def test_one_pass_parser_equals_two_call_packer(tmp_path):
+    """epi_tsv_parse_* (row count not known beforehand, one inflate pass) against epi_tsv_shape + epi_pack_tsv: same labels,
+    pad bytes, coordinates and chromosome table for whole files, row ranges and rank splits; an unterminated last line is
+    not a row in either (the reference counts newline characters); an empty file has no rows."""
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 18, size=(70001, 37)).astype(np.int8)                  # spans three internal 32768-row chunks
+    f = tmp_path / "m.txt.gz"
+    with gzip.open(f, "wt", compresslevel=1) as out:
+        for r in range(len(x)):
+            out.write("chr%d\t%d\t%d\t%s\n" % (1 + r // 40000, r * 200, r * 200 + 200, "\t".join(map(str, (x[r] + 1).tolist()))))
+        out.write("chr2\t1\t2\t" + "\t".join(["1"] * 37))                        # no newline: not a row
+    shape = helpers.tsv_shape(f)
+    assert shape == (70001, 37)
+    for rows in (None, (0, 70001), (32767, 32769), (65536, 70001), (500, 500)):
+        la, a, total = helpers.read_matrix(f, rows, num_states=18, return_total=True)
+        lb, b = helpers.read_matrix(f, rows if rows is not None else (0, 70001), num_states=18, shape=shape)
+        assert total == 70001 and np.array_equal(a, b) and np.array_equal(a.base, b.base)
+        for key in ("start", "end"):
+            assert np.array_equal(la[key], lb[key])
+        assert list(la["chrom"]) == list(lb["chrom"])          # (ids number the file's names in one, the range's in the other)
+        names = la["chrom_names"].split(b"\0")
+        assert [names[i].decode() for i in la["chrom_id"]] == list(la["chrom"])
+    lo, hi = helpers.splitRows(70001, 3)[1]
+    _, part = helpers.read_matrix(f, num_states=18, split=(1, 3), want_locations=False)
+    assert np.array_equal(part, x[lo:hi])
+    e = tmp_path / "empty.txt"
+    e.write_text("")
+    loc, s0, total = helpers.read_matrix(e, num_states=18, return_total=True)
+    assert total == 0 and s0.shape[0] == 0
 
 
 def test_packer_long_lines_across_buffer_blocks(tmp_path):
