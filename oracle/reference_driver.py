@@ -113,3 +113,29 @@ def run_paired(statesA0, statesB0, num_states, saliency, seed, quiescent_state=N
             text = g.read()
         return dict(counts=counts, exp=exp, null_distances=np.array(null), quiescence=np.array(quies),
                     delta_text=text)
+
+
+def run_simsearch(reduced_genome, roi_starts, window_bins, block_size, n_desired):
+    """similaritySearch_calc.runEuclideanDistance (similaritySearch_calc.py:67-123) of the unmodified reference on an
+    in-memory reduced genome; the ROIs are the windows of the genome that start at reduced bins `roi_starts`.
+    Returns the int32 [len(roi_starts), n_desired] array the reference stores in simsearch_indices_*.npy."""
+    import warnings
+    import pandas as pd
+    _import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos import similaritySearch_calc as ssc
+    reduced_genome = np.asarray(reduced_genome)
+    g = len(reduced_genome)
+    n_super = window_bins // block_size
+    nbins = g * block_size
+    genome_coords = pd.DataFrame({"Chromosome": ["chr1"] * nbins, "Start": np.arange(nbins) * 200,
+                                  "End": np.arange(nbins) * 200 + 200})
+    roi_cube = np.stack([reduced_genome[s:s + n_super] for s in roi_starts])
+    roi_coords = pd.DataFrame({"Chromosome": ["chr1"] * len(roi_starts),
+                               "Start": [int(s) * block_size * 200 for s in roi_starts],
+                               "End": [(int(s) * block_size + window_bins) * 200 for s in roi_starts]})
+    out = np.zeros((len(roi_starts), n_desired), dtype=np.int32)
+    ssc._initEuclideanDistance(genome_coords, reduced_genome, roi_coords, roi_cube, out, window_bins, block_size, n_desired)
+    ssc.runEuclideanDistance((0, len(roi_starts)))
+    return out

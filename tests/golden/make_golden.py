@@ -114,6 +114,26 @@ def real_full_case():
     print("wrote real10_chr1_full")
 
 
+def simsearch_case():
+    """similaritySearch_calc.runEuclideanDistance of the reference on a synthetic reduced genome:
+    continuous scores with a flat background on half of the bins (so that the mode of the distances exists, as it does
+    for quiescent stretches of real data), ROIs = windows of the genome itself."""
+    rng = np.random.default_rng(0)
+    g, k, block, window = 4000, 18, 5, 25
+    red = rng.random((g, k)) * rng.random((g, 1))
+    red[rng.random(g) < 0.5] = 0.01
+    # plant near-copies of two ROIs so that some hits pass the half-mode threshold
+    starts = np.array([100, 700, 1500, 2600, 3300])
+    for s, copies in ((100, (900, 2000, 3500)), (2600, (300, 1200))):
+        for c in copies:
+            red[c:c + window // block] = red[s:s + window // block] + rng.normal(0, 1e-3, (window // block, k))
+    out = ref.run_simsearch(red, starts, window, block, 10)
+    deep = ref.run_simsearch(red, starts[:2], window, block, 600)          # long lists: ends in the -1 (threshold) branch
+    np.savez_compressed(HERE / "simsearch_g4000_k18.npz", reduced_genome=red, roi_starts=starts, window_bins=np.int64(window),
+                        block_size=np.int64(block), n_desired=np.int64(10), indices=out, indices_deep=deep)
+    print("wrote simsearch_g4000_k18", out[:, :4].tolist())
+
+
 def roi_cases():
     """helpers.maxMean of the reference (the ROI selector that consumes the single-mode scores) on
     (a) S1 scores of a 200 000-bin real-data slice, window 50, and (b) two short synthetic chromosomes with odd /
@@ -188,6 +208,8 @@ def main():
         roi_cases()
     if want("real_full"):
         real_full_case()
+    if want("simsearch"):
+        simsearch_case()
 
 
 if __name__ == "__main__":

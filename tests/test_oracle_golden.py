@@ -136,3 +136,21 @@ def test_full_real_chr1_matches_reference_digests(golden):
     assert np.array_equal(sel["original_idx"], g["roi_original_idx"])          # the reference's own top-100 ranking
     assert np.array_equal(sel["start"], g["roi_start"]) and np.array_equal(sel["end"], g["roi_end"])
     assert sel["rolling_max"].tobytes() == g["roi_rolling_max"].tobytes()
+
+
+def test_simsearch_oracle_matches_reference(golden):
+    """SURVEY.md 8f row f4 (no product code yet): the restatement of similaritySearch_calc.runEuclideanDistance reproduces
+    the unmodified reference's picks, including the threshold stop (-1 fill) of long result lists."""
+    from oracle import simsearch_oracle as so
+    g = golden("simsearch_g4000_k18")
+    red = g["reduced_genome"]
+    n = int(g["window_bins"]) // int(g["block_size"])
+    for r, s in enumerate(g["roi_starts"]):
+        assert np.array_equal(so.similar_regions(red, red[s:s + n], int(s), int(g["n_desired"])), g["indices"][r])
+    for r, s in enumerate(g["roi_starts"][:2]):
+        deep = so.similar_regions(red, red[s:s + n], int(s), g["indices_deep"].shape[1])
+        assert np.array_equal(deep, g["indices_deep"][r]) and (deep == -1).any()
+    d = so.window_distances(red, red[100:100 + n])
+    # (the self-distance is ~1e-17, not 0: XX + YY - 2 X.Y^T rounds, which is why the reference excludes the ROI by position)
+    assert d.shape == (len(red) - n + 1,) and np.argmin(d) == 100 and d[100] < 1e-12
+    assert so.float_mode(np.array([3.0, 1.0, 3.0, 1.0, 2.0])) == 1.0
