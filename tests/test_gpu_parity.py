@@ -164,6 +164,33 @@ def test_tensor_core_tables_and_scores_edge_shapes(eng, bins, cols, k):
     assert_f32_close(t32.cpu().numpy(), ref1.astype(np.float32), max_ulp_frac=1e-4)
 
 
+@pytest.mark.parametrize("bins,cols,k,kind", [(4_200_000, 833, 18, "realistic"), (2_000_000, 127, 15, "realistic"),
+                                              (300_000, 833, 18, "uniform"), (70_000, 200, 32, "uniform")])
+def test_tensor_core_kernels_against_the_pipes_they_replace(eng, monkeypatch, bins, cols, k, kind):
+    """A/B at sizes that run many tiles per CTA, several accumulator drains and every warpgroup slot: the tensor-core K2
+    must equal the integer-pipe K2 bit for bit, the tensor-core K5 must agree with the fp64-pipe TABLE kernel within the
+    score tolerance, and its float32 output must be the rounding of its float64 output.  (EPI_K2_ALU / EPI_K5_ALU are
+    read on every call.)"""
+    from epilogos_b200 import synth
+    x = synth.synth_states_device(bins, cols, k, seed=bins % 97, kind=kind)
+    cnt = eng.bin_counts(x, cols, k)
+    del x
+    monkeypatch.setenv("EPI_K2_ALU", "1")
+    monkeypatch.setenv("EPI_K5_ALU", "1")
+    n1a, n2a = eng.expected_tables(cnt, cols)
+    e2 = eng.normalize(n2a)
+    _, ref64 = eng.scores_s2(cnt, cols, e2, want64=True)
+    monkeypatch.delenv("EPI_K2_ALU")
+    monkeypatch.delenv("EPI_K5_ALU")
+    n1t, n2t = eng.expected_tables(cnt, cols)
+    assert torch.equal(n1a, n1t) and torch.equal(n2a, n2t)
+    assert int(n1t.sum()) == bins * cols and int(n2t.sum()) == bins * cols * (cols - 1)
+    s32, s64 = eng.scores_s2(cnt, cols, e2, want64=True)
+    a, b = ref64.cpu().numpy(), s64.cpu().numpy()
+    assert np.all(np.abs(a - b) <= RTOL * np.abs(a) + ATOL)
+    assert np.array_equal(s32.cpu().numpy(), b.astype(np.float32))
+
+
 def test_foreign_expected_table_with_zeros_is_masked(eng):
     """klScoreND masks terms whose expected frequency is 0 (scores.py:550); a table computed from other
     data can have zeros where this data has observations."""
