@@ -194,6 +194,20 @@ int epi_roi_maxmean(const double* score, const int64_t* starts, const int64_t* e
                     int32_t max_regions, int64_t* out_original_idx, int64_t* out_start, int64_t* out_end,
                     double* out_rolling_max, double* out_rolling_mean, int32_t* n_out);
 
+/* ---- similarity-search distance engine (similaritySearch_calc.runEuclideanDistance, similaritySearch_calc.py:67-123) --
+ * For every ROI r (nS reduced bins x K states, row-major [R][nS][K] float64) and every window w of the reduced genome
+ * ([G][K] float64):  dist[r][w] = sum_j max(0, ((-2 X[w+j].Y_r[j]) + XX[w+j]) + YY_r[j]),  w < W = G - nS + 1 -- sklearn's
+ * euclidean_distances(squared=True) gathered along diagonals and summed (similaritySearch_calc.py:86-99).
+ *   epi_simsearch_row_norms    XX[a] = |X[a]|^2, once per genome
+ *   epi_simsearch_distances    dist for a batch of ROIs (float64 [R][W])
+ *   epi_simsearch_mode_sorted  scipy.stats.mode of every row of an ASCENDING float64 [R][W] array (most frequent value,
+ *                              the smallest among ties; :101): the acceptance threshold is half of it; count_dev may be NULL */
+int epi_simsearch_row_norms(const double* genome_dev, int64_t G, int32_t K, double* xx_dev, void* stream);
+int epi_simsearch_distances(const double* genome_dev, const double* xx_dev, int64_t G, int32_t K, const double* rois_dev,
+                            int32_t R, int32_t nS, double* dist_dev, void* stream);
+int epi_simsearch_mode_sorted(const double* sorted_dev, int32_t R, int64_t W, double* mode_dev, int64_t* count_dev,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif
