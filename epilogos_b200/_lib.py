@@ -44,6 +44,8 @@ PROTOTYPES = {
     "epi_simsearch_row_norms": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "epi_simsearch_distances": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "epi_simsearch_mode_sorted": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "epi_simsearch_pick": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                   c_void_p]),
     "epi_tsv_shape": (c_int, [c_char_p, POINTER(c_int64), POINTER(c_int32)]),
     "epi_tsv_parse_open": (c_int, [c_char_p, c_int32, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
                                    POINTER(c_int32), POINTER(c_int32)]),

@@ -84,14 +84,19 @@ __global__ void __launch_bounds__(256) ss_mode_kernel(const double* __restrict__
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < W; i += (long long)gridDim.x * blockDim.x) {
         const double x = v[i];
         if (i + 1 < W && v[i + 1] == x) continue;               // not the end of a run
-        long long lo = 0, hi = i;                                // first index with v[idx] == x  (v ascending)
+        long long lo = i, hi = i;
+        if (i > 0 && v[i - 1] == x) lo = 0;                      // a run of more than one value: search its start
+        // first index with v[idx] == x  (v ascending); runs of one (almost every value of real distances) skip the search
         while (lo < hi) {
             const long long mid = (lo + hi) >> 1;
             if (v[mid] < x) lo = mid + 1;
             else hi = mid;
         }
         const unsigned long long len = (unsigned long long)(i - lo + 1);
-        atomicMax(&best[blockIdx.y], (len << 32) | (0xffffffffull - (unsigned long long)lo));
+        const unsigned long long key = (len << 32) | (0xffffffffull - (unsigned long long)lo);
+        // almost every run is a single value and loses against the current best: look before the atomic (3 M atomics on
+        // one address cost 2 ms per ROI; the racy read only ever skips keys that could not have won)
+        if (key > *reinterpret_cast<volatile unsigned long long*>(&best[blockIdx.y])) atomicMax(&best[blockIdx.y], key);
     }
 }
 
@@ -105,9 +110,67 @@ __global__ void ss_mode_value_kernel(const double* __restrict__ sorted, long lon
     if (count != nullptr) count[r] = (long long)(b >> 32);
 }
 
+// similaritySearch_calc.py:103-123 -- one warp per ROI walks its windows in increasing distance (svals / sidx: the sorted
+// distances and their window indices) and picks up to n_desired windows that do not overlap the ROI itself or an earlier
+// pick (|hit - a| < nS  <=>  np.any(overlapArr[hit : hit + nS])); the first admissible window farther than mode / 2 ends
+// the list with -1.  The output row starts as zeros, as the reference's array does.
+__global__ void __launch_bounds__(128) ss_greedy_kernel(const double* __restrict__ svals, const long long* __restrict__ sidx,
+                                                        long long W, const double* __restrict__ mode,
+                                                        const long long* __restrict__ region_start, int nS, int n_desired,
+                                                        int R, int* __restrict__ out) {
+    const int r = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double* v = svals + (long long)r * W;
+    const long long* ix = sidx + (long long)r * W;
+    int* row = out + (long long)r * n_desired;
+    for (int i = lane; i < n_desired; i += 32) row[i] = 0;
+    __syncwarp();
+    const double half_mode = mode[r] / 2;
+    const long long self = region_start[r];
+    int found = 0;
+    for (long long pos0 = 0; pos0 < W; pos0 += 32) {
+        // 32 candidates per coalesced load, handed round by shuffles (the walk itself is sequential: a pick blocks later ones)
+        const long long my_hit = pos0 + lane < W ? ix[pos0 + lane] : 0;
+        const double my_d = pos0 + lane < W ? v[pos0 + lane] : 0.0;
+        const int n = (W - pos0) < 32 ? (int)(W - pos0) : 32;
+        for (int j = 0; j < n; ++j) {
+            const long long hit = __shfl_sync(0xffffffffu, my_hit, j);
+            const double d = __shfl_sync(0xffffffffu, my_d, j);
+            bool clash = false;
+            if (lane == 0) clash = llabs(hit - self) < nS;
+            for (int i = lane; i < found; i += 32) clash |= llabs(hit - (long long)row[i]) < nS;
+            if (__any_sync(0xffffffffu, clash)) continue;
+            if (d > half_mode) {
+                for (int i = found + lane; i < n_desired; i += 32) row[i] = -1;
+                return;
+            }
+            if (lane == 0) row[found] = (int)hit;
+            __syncwarp();
+            if (++found >= n_desired) return;
+        }
+    }
+}
+
 }  // namespace epi
 
 using namespace epi;
+
+extern "C" int epi_simsearch_pick(const double* sorted_dev, const int64_t* index_dev, int32_t R, int64_t W,
+                                  const double* mode_dev, const int64_t* region_start_dev, int32_t nS, int32_t n_desired,
+                                  int32_t* out_dev, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(R >= 0 && W >= 1 && nS >= 1 && n_desired >= 1, "bad shape");
+    if (R == 0) return 0;
+    EPI_REQUIRE(sorted_dev != nullptr && index_dev != nullptr && mode_dev != nullptr && region_start_dev != nullptr &&
+                    out_dev != nullptr, "null pointer argument");
+    ss_greedy_kernel<<<(R * 32 + 127) / 128, 128, 0, st>>>(sorted_dev, reinterpret_cast<const long long*>(index_dev), W, mode_dev,
+                                                          reinterpret_cast<const long long*>(region_start_dev), nS, n_desired, R,
+                                                          out_dev);
+    EPI_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int epi_simsearch_row_norms(const double* genome_dev, int64_t G, int32_t K, double* xx_dev, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);

@@ -4,10 +4,10 @@ squared Euclidean distance to every window of `reduced_genome.npy`, half the mod
 threshold, and a greedy pick of up to nDesiredMatches non-overlapping windows in increasing distance.  Writes
 `simsearch_indices_<processTag>.npy` (int32 [regions, nDesiredMatches]; -1 after a threshold stop) like the reference.
 
-The distances of a batch of ROIs are computed on the GPU (csrc/simsearch.cu), sorted there, the mode is read off the
-sorted rows there, and only the leading candidates of every ROI come back to the host for the (inherently sequential,
-<= nDesiredMatches long) greedy pick.  `nCores` is accepted and ignored.  Ties: the reference visits exactly tied
-distances in the order of numpy's unstable introsort; here ties are visited in ascending window index.
+Everything runs on the GPU per batch of ROIs (csrc/simsearch.cu): distances, the sort (torch.sort = a library radix
+sort, plumbing), the mode read off the sorted rows, and the greedy pick (one warp per ROI); only the int32 result rows
+come back.  `nCores` is accepted and ignored.  Ties: the reference visits exactly tied distances in the order of numpy's
+unstable introsort; here ties are visited in ascending window index.
 """
 import ctypes
 import sys
@@ -56,30 +56,14 @@ def mode_of_sorted(sorted_dev):
     return mode
 
 
-def _greedy(vals, idx, fetch_more, half_mode, region_start, n_super, n_desired):
-    """similaritySearch_calc.py:103-123 over candidates in increasing distance; `fetch_more(n)` extends (vals, idx)."""
-    out = np.zeros(n_desired, dtype=np.int32)
-    taken = [region_start]                              # starts of blocked windows: the ROI itself, then every pick
-    found, pos = 0, 0
-    while True:
-        if pos >= len(vals):
-            more = fetch_more(len(vals))
-            if more is None:
-                return out
-            vals, idx = more
-            continue
-        hit, d = int(idx[pos]), vals[pos]
-        pos += 1
-        if any(abs(hit - a) < n_super for a in taken):   # np.any(overlapArr[hitIndex:hitIndex + nSuperBins])
-            continue
-        if d > half_mode:
-            out[found:] = -1
-            return out
-        out[found] = hit
-        taken.append(hit)
-        found += 1
-        if found >= n_desired:
-            return out
+def pick(sorted_dev, index_dev, mode_dev, region_start_dev, n_super, n_desired):
+    """The greedy selection (similaritySearch_calc.py:103-123) for every row: int32 CUDA tensor [R, n_desired]."""
+    import torch
+    r, w = sorted_dev.shape
+    out = torch.empty((r, n_desired), dtype=torch.int32, device=sorted_dev.device)
+    _lib.call("epi_simsearch_pick", _ptr(sorted_dev), _ptr(index_dev.contiguous()), r, w, _ptr(mode_dev),
+              _ptr(region_start_dev.contiguous()), int(n_super), int(n_desired), _ptr(out), _stream())
+    return out
 
 
 def _region_starts(genome_coords, roi_coords, block_size):
@@ -123,20 +107,14 @@ def euclideanDistanceMulti(outputDir, genomeCoords, roiCoords, roiCube, windowBi
     genome = torch.from_numpy(np.ascontiguousarray(reduced)).cuda()
     xx = row_norms(genome)
     cube = np.ascontiguousarray(np.asarray(roiCube)[lo:hi], dtype=np.float64)
-    first = min(4096, genome.shape[0] - n_super + 1)
+    starts_dev = torch.from_numpy(starts).cuda()
     for b0 in range(0, n_regions, ROI_BATCH):
         rois = torch.from_numpy(cube[b0:b0 + ROI_BATCH]).cuda()
         dist = window_distances(genome, xx, rois)
         svals, sidx = torch.sort(dist, dim=1, stable=True)
-        half = (mode_of_sorted(svals) / 2).cpu().numpy()
-        hv, hi_ = svals[:, :first].cpu().numpy(), sidx[:, :first].cpu().numpy()
-        for q in range(rois.shape[0]):
-            def fetch_more(have, q=q):
-                if have >= svals.shape[1]:
-                    return None
-                n = min(svals.shape[1], max(4 * have, 1))
-                return svals[q, :n].cpu().numpy(), sidx[q, :n].cpu().numpy()
-            result[b0 + q] = _greedy(hv[q], hi_[q], fetch_more, half[q], int(starts[b0 + q]), n_super, nDesiredMatches)
+        mode = mode_of_sorted(svals)
+        picks = pick(svals, sidx, mode, starts_dev[b0:b0 + rois.shape[0]], n_super, nDesiredMatches)
+        result[b0:b0 + rois.shape[0]] = picks.cpu().numpy()
     np.save(outputDir / "simsearch_indices_{}.npy".format(processTag), result, allow_pickle=True)
     return result
 

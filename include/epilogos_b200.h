@@ -201,12 +201,18 @@ int epi_roi_maxmean(const double* score, const int64_t* starts, const int64_t* e
  *   epi_simsearch_row_norms    XX[a] = |X[a]|^2, once per genome
  *   epi_simsearch_distances    dist for a batch of ROIs (float64 [R][W])
  *   epi_simsearch_mode_sorted  scipy.stats.mode of every row of an ASCENDING float64 [R][W] array (most frequent value,
- *                              the smallest among ties; :101): the acceptance threshold is half of it; count_dev may be NULL */
+ *                              the smallest among ties; :101): the acceptance threshold is half of it; count_dev may be NULL
+ *   epi_simsearch_pick         the greedy selection (:103-123) on the device: windows in increasing distance (sorted_dev /
+ *                              index_dev = sorted distances and their window indices, [R][W]), no overlap with the ROI itself
+ *                              (region_start_dev, reduced bins) or an earlier pick, -1 fill after the first admissible
+ *                              window farther than mode / 2; out_dev int32 [R][n_desired] */
 int epi_simsearch_row_norms(const double* genome_dev, int64_t G, int32_t K, double* xx_dev, void* stream);
 int epi_simsearch_distances(const double* genome_dev, const double* xx_dev, int64_t G, int32_t K, const double* rois_dev,
                             int32_t R, int32_t nS, double* dist_dev, void* stream);
 int epi_simsearch_mode_sorted(const double* sorted_dev, int32_t R, int64_t W, double* mode_dev, int64_t* count_dev,
                               void* stream);
+int epi_simsearch_pick(const double* sorted_dev, const int64_t* index_dev, int32_t R, int64_t W, const double* mode_dev,
+                       const int64_t* region_start_dev, int32_t nS, int32_t n_desired, int32_t* out_dev, void* stream);
 
 #ifdef __cplusplus
 }
