@@ -115,7 +115,17 @@ def run_paired(statesA0, statesB0, num_states, saliency, seed, quiescent_state=N
                     delta_text=text)
 
 
-def run_simsearch(reduced_genome, roi_starts, window_bins, block_size, n_desired):
+def simsearch_coords(nbins, chrom_split=None):
+    """Coordinates of the non-reduced genome of the similarity-search fixtures: one chromosome, or chr1 = the first
+    `chrom_split` bins and chr2 the rest (coordinates restart at 0 on chr2, so a start alone does not identify a bin)."""
+    if chrom_split is None:
+        return np.array(["chr1"] * nbins, dtype=object), np.arange(nbins, dtype=np.int64) * 200
+    chrom = np.array(["chr1"] * chrom_split + ["chr2"] * (nbins - chrom_split), dtype=object)
+    start = np.concatenate((np.arange(chrom_split), np.arange(nbins - chrom_split))).astype(np.int64) * 200
+    return chrom, start
+
+
+def run_simsearch(reduced_genome, roi_starts, window_bins, block_size, n_desired, chrom_split=None):
     """similaritySearch_calc.runEuclideanDistance (similaritySearch_calc.py:67-123) of the unmodified reference on an
     in-memory reduced genome; the ROIs are the windows of the genome that start at reduced bins `roi_starts`.
     Returns the int32 [len(roi_starts), n_desired] array the reference stores in simsearch_indices_*.npy."""
@@ -129,12 +139,12 @@ def run_simsearch(reduced_genome, roi_starts, window_bins, block_size, n_desired
     g = len(reduced_genome)
     n_super = window_bins // block_size
     nbins = g * block_size
-    genome_coords = pd.DataFrame({"Chromosome": ["chr1"] * nbins, "Start": np.arange(nbins) * 200,
-                                  "End": np.arange(nbins) * 200 + 200})
+    chrom, start = simsearch_coords(nbins, chrom_split)
+    genome_coords = pd.DataFrame({"Chromosome": chrom, "Start": start, "End": start + 200})
     roi_cube = np.stack([reduced_genome[s:s + n_super] for s in roi_starts])
-    roi_coords = pd.DataFrame({"Chromosome": ["chr1"] * len(roi_starts),
-                               "Start": [int(s) * block_size * 200 for s in roi_starts],
-                               "End": [(int(s) * block_size + window_bins) * 200 for s in roi_starts]})
+    rows = [int(s) * block_size for s in roi_starts]
+    roi_coords = pd.DataFrame({"Chromosome": [chrom[r] for r in rows], "Start": [int(start[r]) for r in rows],
+                               "End": [int(start[r]) + window_bins * 200 for r in rows]})
     out = np.zeros((len(roi_starts), n_desired), dtype=np.int32)
     ssc._initEuclideanDistance(genome_coords, reduced_genome, roi_coords, roi_cube, out, window_bins, block_size, n_desired)
     ssc.runEuclideanDistance((0, len(roi_starts)))

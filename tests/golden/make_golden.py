@@ -132,6 +132,22 @@ def simsearch_case():
     np.savez_compressed(HERE / "simsearch_g4000_k18.npz", reduced_genome=red, roi_starts=starts, window_bins=np.int64(window),
                         block_size=np.int64(block), n_desired=np.int64(10), indices=out, indices_deep=deep)
     print("wrote simsearch_g4000_k18", out[:, :4].tolist())
+    # second shape: 15 states, windows of 3 reduced bins (blockSize 2), two chromosomes whose coordinates restart
+    rng = np.random.default_rng(1)
+    g, k, block, window, split = 5000, 15, 2, 6, 6000
+    red = rng.random((g, k)) ** 2
+    red[rng.random(g) < 0.4] = 0.005                             # flat stretches: the mode of the distances
+    starts = np.array([40, 2999, 3000, 3500, 4990])              # 2999: the window straddles the chromosome boundary
+    for s in starts:                                             # the ROIs themselves are not flat (no exactly tied picks:
+        red[s:s + window // block] = rng.random((window // block, k)) ** 2      # their order is numpy-introsort specific)
+    for s, copies in ((3500, (100, 4200)), (40, (700,))):
+        for c in copies:
+            red[c:c + window // block] = red[s:s + window // block] * (1 + rng.normal(0, 1e-4, (window // block, k)))
+    out = ref.run_simsearch(red, starts, window, block, 25, chrom_split=split)
+    np.savez_compressed(HERE / "simsearch_g5000_k15_2chrom.npz", reduced_genome=red, roi_starts=starts,
+                        window_bins=np.int64(window), block_size=np.int64(block), n_desired=np.int64(25), indices=out,
+                        chrom_split=np.int64(split))
+    print("wrote simsearch_g5000_k15_2chrom", out[:, :4].tolist(), (out == -1).sum(axis=1).tolist())
 
 
 def roi_cases():

@@ -150,6 +150,11 @@ def test_simsearch_oracle_matches_reference(golden):
     for r, s in enumerate(g["roi_starts"][:2]):
         deep = so.similar_regions(red, red[s:s + n], int(s), g["indices_deep"].shape[1])
         assert np.array_equal(deep, g["indices_deep"][r]) and (deep == -1).any()
+    g2 = golden("simsearch_g5000_k15_2chrom")                 # 15 states, 3-bin windows, every list ends by the threshold
+    red2, n2 = g2["reduced_genome"], int(g2["window_bins"]) // int(g2["block_size"])
+    for r, s in enumerate(g2["roi_starts"]):
+        got = so.similar_regions(red2, red2[s:s + n2], int(s), int(g2["n_desired"]))
+        assert np.array_equal(got, g2["indices"][r]) and (got == -1).any()
     d = so.window_distances(red, red[100:100 + n])
     # (the self-distance is ~1e-17, not 0: XX + YY - 2 X.Y^T rounds, which is why the reference excludes the ROI by position)
     assert d.shape == (len(red) - n + 1,) and np.argmin(d) == 100 and d[100] < 1e-12

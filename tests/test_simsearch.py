@@ -9,15 +9,21 @@ from oracle import simsearch_oracle as so            # noqa: E402  (checker only
 
 
 def _write_inputs(d, g, starts, n_super, block):
+    """genome_stats.npz / simsearch_cube.npz / reduced_genome.npy as similaritySearch_max_mean writes them; coordinates as
+    in oracle/reference_driver.simsearch_coords (two chromosomes whose coordinates restart, if the fixture has a split)."""
     red = g["reduced_genome"]
     nbins = len(red) * block
+    split = int(g["chrom_split"]) if "chrom_split" in g.files else nbins
     coords = np.empty((nbins, 3), dtype=object)
-    coords[:, 0] = "chr1"; coords[:, 1] = np.arange(nbins) * 200; coords[:, 2] = np.arange(nbins) * 200 + 200
+    coords[:, 0] = ["chr1"] * split + ["chr2"] * (nbins - split)
+    coords[:, 1] = np.concatenate((np.arange(split), np.arange(nbins - split))) * 200
+    coords[:, 2] = coords[:, 1] + 200
     np.savez_compressed(d / "genome_stats", scores=np.zeros((1, 1)), coords=coords)
+    rows = [int(s) * block for s in starts]
     roi_coords = np.empty((len(starts), 3), dtype=object)
-    roi_coords[:, 0] = "chr1"
-    roi_coords[:, 1] = [int(s) * block * 200 for s in starts]
-    roi_coords[:, 2] = [(int(s) * block + n_super * block) * 200 for s in starts]
+    roi_coords[:, 0] = [coords[r, 0] for r in rows]
+    roi_coords[:, 1] = [coords[r, 1] for r in rows]
+    roi_coords[:, 2] = [coords[r, 1] + n_super * block * 200 for r in rows]
     np.savez_compressed(d / "simsearch_cube", scores=np.stack([red[s:s + n_super] for s in starts]), coords=roi_coords)
     np.save(d / "reduced_genome.npy", red)
 
@@ -47,6 +53,21 @@ def test_simsearch_matches_reference_golden(golden, tmp_path):
     modes = ssc.mode_of_sorted(svals).cpu().numpy()
     for r in range(len(starts)):
         assert modes[r] == so.float_mode(dist[r])
+
+
+def test_simsearch_two_chromosomes_and_threshold_stops(golden, tmp_path):
+    """15 states, 3-bin windows, ROIs on both chromosomes (coordinates restart on chr2, one window straddles the boundary):
+    the region-start look-up and the -1 fill of every list against the reference's picks; rows split over two jobs."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from epilogos_b200 import similaritySearch_calc as ssc
+    g = golden("simsearch_g5000_k15_2chrom")
+    window, block = int(g["window_bins"]), int(g["block_size"])
+    _write_inputs(tmp_path, g, g["roi_starts"], window // block, block)
+    a = ssc.main(tmp_path, window, block, 0, int(g["n_desired"]), 2, 0)
+    b = ssc.main(tmp_path, window, block, 0, int(g["n_desired"]), 2, 1)
+    assert np.array_equal(np.concatenate((a, b)), g["indices"])
+    assert np.array_equal(np.load(tmp_path / "simsearch_indices_1.npy"), b)
 
 
 def test_mode_of_sorted_edge_cases():
