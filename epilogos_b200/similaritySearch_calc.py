@@ -67,25 +67,37 @@ def pick(sorted_dev, index_dev, mode_dev, region_start_dev, n_super, n_desired):
 
 
 def _region_starts(genome_coords, roi_coords, block_size):
-    """Row of the non-reduced genome where each ROI starts, // blockSize (similaritySearch_calc.py:107-109)."""
+    """Row of the non-reduced genome where each ROI starts, // blockSize (similaritySearch_calc.py:107-109: the FIRST row
+    whose chromosome and start match).  The genome is cut into runs of equal chromosome once (O(rows)); a ROI is looked up
+    by binary search inside the runs of its chromosome when their starts ascend, by a scan otherwise."""
     chrom = np.asarray(genome_coords[:, 0]).astype(str)
     start = np.asarray(genome_coords[:, 1]).astype(np.int64)
-    order = np.lexsort((start, chrom))
-    key_c, key_s = chrom[order], start[order]
+    n = len(chrom)
+    cuts = np.flatnonzero(chrom[1:] != chrom[:-1]) + 1 if n > 1 else np.array([], dtype=np.int64)
+    bounds = np.concatenate(([0], cuts, [n])).astype(np.int64)
+    runs = {}
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        if hi > lo:
+            seg = start[lo:hi]
+            runs.setdefault(chrom[lo], []).append((int(lo), int(hi), bool(np.all(seg[1:] >= seg[:-1]))))
     out = np.empty(len(roi_coords), dtype=np.int64)
     for r in range(len(roi_coords)):
         c, s = str(roi_coords[r, 0]), int(roi_coords[r, 1])
-        lo = np.searchsorted(key_c, c, side="left")
-        hi = np.searchsorted(key_c, c, side="right")
-        p = lo + np.searchsorted(key_s[lo:hi], s, side="left")
-        if p >= hi or key_s[p] != s:
+        found = -1
+        for lo, hi, ascending in runs.get(c, ()):
+            if ascending:
+                p = lo + int(np.searchsorted(start[lo:hi], s, side="left"))
+                if p < hi and start[p] == s:
+                    found = p
+            else:
+                hits = np.flatnonzero(start[lo:hi] == s)
+                if len(hits):
+                    found = lo + int(hits[0])
+            if found >= 0:
+                break
+        if found < 0:
             raise IndexError("region %s:%d is not a bin of genome_stats.npz" % (c, s))
-        first = order[p]
-        # the reference takes the FIRST matching row in file order
-        while p + 1 < hi and key_s[p + 1] == s:
-            p += 1
-            first = min(first, order[p])
-        out[r] = first // block_size
+        out[r] = found // block_size
     return out
 
 

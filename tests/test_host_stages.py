@@ -113,6 +113,22 @@ def test_prefetch_parses_every_file_once_and_stages_reuse_it(tmp_path, golden, m
     session.clear()
 
 
+def test_simsearch_region_start_lookup():
+    """similaritySearch_calc.py:107-109: the first genome row whose chromosome AND start match, // blockSize -- with
+    chromosomes whose coordinates restart, a chromosome that appears in two separate runs, and unsorted starts."""
+    from epilogos_b200.similaritySearch_calc import _region_starts
+    chrom = np.array(["chr1"] * 6 + ["chr2"] * 5 + ["chr1"] * 3 + ["chrX"] * 4, dtype=object)
+    start = np.array([0, 200, 400, 600, 800, 1000, 0, 200, 400, 600, 800, 5000, 5200, 5400, 600, 200, 400, 0])
+    coords = np.empty((len(chrom), 3), dtype=object)
+    coords[:, 0], coords[:, 1], coords[:, 2] = chrom, start, start + 200
+    rois = np.array([["chr1", 400, 0], ["chr2", 400, 0], ["chr1", 5200, 0], ["chrX", 200, 0], ["chr2", 0, 0]], dtype=object)
+    want = [int(np.flatnonzero((chrom == c) & (start == s))[0]) for c, s, _ in rois]
+    assert _region_starts(coords, rois, 1).tolist() == want == [2, 8, 12, 15, 6]
+    assert _region_starts(coords, rois, 5).tolist() == [w // 5 for w in want]
+    with pytest.raises(IndexError):
+        _region_starts(coords, np.array([["chr2", 5000, 0]], dtype=object), 1)
+
+
 def test_bad_saliency_raises(tmp_path):
     from fake_backend import OracleBackend
     from epilogos_b200 import expected
