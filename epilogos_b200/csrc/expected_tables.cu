@@ -1,4 +1,7 @@
 // K2 (S1/S2 expected count tables from the per-bin counts) and K4 (normalise).
+// The K2 in this file is the integer-ALU kernel; epi_expected_s1s2 runs the tensor-core Gram kernel of
+// tc_tables.cu (every K <= 32) and keeps this one behind EPI_K2_ALU=1 for A/B timing and as the
+// cross-check of the tests: both produce the same int64 tables bit for bit (tests/test_gpu_parity.py).
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -21,6 +21,13 @@
 //
 // I/O is staged per warp (no block-wide barriers in the steady state): 32 bins of counts come in as 16-byte
 // vectors, 32 rows of float32 scores leave as 16-byte vectors.
+//
+// Dispatch (dispatch_s2 below): with width <= 2047 the S2 TABLE evaluation runs on the tensor cores
+// (tc_tables.cu: the (LE c) mat-vec as an exact int8 tcgen05 product of the count bytes with base-256 digits
+// of -log2 E); the DFMA TABLE kernel in this file is the path for wider inputs and for EPI_K5_ALU=1, and the
+// DIRECT kernel is queued behind either, gated on the device-side "table has a zero" flag.
+// S1 needs no re-association at all: its K x (width+1) value table is built with the reference expression
+// itself (k5_s1_table_kernel), so S1 scores are bit-equal to the float64 reference before the float32 cast.
 #include <stdlib.h>
 
 #include "common.cuh"
