@@ -5,6 +5,7 @@
 //   epi_pack_tsv         rows [lo, hi) of `chr start end s_1 .. s_C` -> int8 labels-1 in the kernels' pitched
 //                        layout + start/end/chromosome per row (replaces the pandas parse of helpers.readStates,
 //                        helpers.py:150-168, and of scores.py:161); labels are validated here
+//   epi_scores_tsv_*     score text back into float64 rows (similaritySearch_max_mean.readScores, :51-74)
 //   epi_write_scores_gz  `chr \t start \t end \t K x "%.5f"` lines through gzip (scores.writeScores,
 //                        scores.py:509-536): rows are formatted and deflated in parallel as independent gzip
 //                        members (a valid multi-member .gz; the decompressed text is byte-identical to the
@@ -417,6 +418,161 @@ extern "C" int epi_tsv_parse_fetch(void* handle, int64_t row_lo, int64_t row_hi,
 
 extern "C" int epi_tsv_parse_close(void* handle) {
     delete static_cast<ParsedFile*>(handle);
+    return 0;
+}
+
+// ---- score text (`chr \t start \t end \t K decimal fields`, the files epi_write_scores_gz / scores.writeScores produce)
+//      back into float64: replaces the pandas read of similaritySearch_max_mean.readScores (:51-74) ---------------------
+namespace epi {
+struct ScoreFile {
+    static constexpr int64_t CHUNK_ROWS = 1 << 15;
+    int32_t cols = 0;
+    int64_t rows = 0;
+    std::vector<std::vector<double>> vals;        // chunks of CHUNK_ROWS x cols
+    std::vector<int64_t> starts, ends;
+    std::vector<int32_t> chrom;
+    std::vector<std::string> names;
+};
+
+// One decimal field [p, e) -> the nearest double.  Plain decimals with at most 15 significant digits are an exactly
+// representable integer divided by an exactly representable power of ten, i.e. one correctly rounded division; anything
+// else (exponents, nan, inf, longer mantissas) goes through strtod.
+static inline bool parse_decimal(const char* p, const char* e, double* out) {
+    static const double p10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                                 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char* q = p;
+    bool neg = false;
+    if (q < e && (*q == '-' || *q == '+')) neg = (*q++ == '-');
+    unsigned long long mant = 0;
+    int digits = 0, frac = 0;
+    const char* d0 = q;
+    while (q < e && (unsigned)(*q - '0') <= 9 && digits < 19) {
+        mant = mant * 10 + (unsigned)(*q++ - '0');
+        if (mant) ++digits;
+    }
+    int nd = (int)(q - d0);
+    if (q < e && *q == '.') {
+        ++q;
+        const char* f0 = q;
+        while (q < e && (unsigned)(*q - '0') <= 9 && digits < 19) {
+            mant = mant * 10 + (unsigned)(*q++ - '0');
+            if (mant) ++digits;
+        }
+        frac = (int)(q - f0);
+        nd += frac;
+    }
+    if (q == e && nd > 0 && digits <= 15 && frac <= 22) {
+        const double v = (double)mant / p10[frac];
+        *out = neg ? -v : v;
+        return true;
+    }
+    char tmp[64];
+    const size_t n = (size_t)(e - p);
+    if (n == 0 || n >= sizeof(tmp)) return false;
+    memcpy(tmp, p, n);
+    tmp[n] = 0;
+    char* endp = nullptr;
+    *out = strtod(tmp, &endp);
+    return endp == tmp + n;
+}
+}  // namespace epi
+
+extern "C" int epi_scores_tsv_open(const char* path, void** handle_out, int64_t* rows_out, int32_t* cols_out,
+                                   int32_t* n_chrom_out, int32_t* names_bytes_out) {
+    EPI_REQUIRE(path != nullptr && handle_out != nullptr, "null pointer argument");
+    LineSource src;
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    std::unique_ptr<ScoreFile> sf(new ScoreFile());
+    const char *p, *e;
+    bool has_nl;
+    int last_id = -1;
+    while (src.next_line(p, e, has_nl)) {
+        if (e > p && e[-1] == '\r') --e;
+        if (p == e) continue;                           // blank lines are skipped, as the pandas reader does
+        const int64_t r = sf->rows;
+        if (r == 0) {
+            int tabs = 0;
+            for (const char* q = p; q < e; ++q) tabs += (*q == '\t');
+            sf->cols = tabs + 1 - 3;
+            EPI_REQUIRE(sf->cols >= 1, "%s: expected `chr start end score_1 ...` rows", path);
+        }
+        if (r % ScoreFile::CHUNK_ROWS == 0) sf->vals.emplace_back((size_t)ScoreFile::CHUNK_ROWS * sf->cols);
+        double* dst = sf->vals.back().data() + (r % ScoreFile::CHUNK_ROWS) * sf->cols;
+        // chromosome
+        const char* t = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
+        EPI_REQUIRE(t != nullptr, "%s: row %lld is truncated", path, (long long)r);
+        {
+            const size_t nl = (size_t)(t - p);
+            int id = -1;
+            if (last_id >= 0 && sf->names[last_id].size() == nl && memcmp(sf->names[last_id].data(), p, nl) == 0) id = last_id;
+            for (size_t i = 0; id < 0 && i < sf->names.size(); ++i)
+                if (sf->names[i].size() == nl && memcmp(sf->names[i].data(), p, nl) == 0) id = (int)i;
+            if (id < 0) {
+                id = (int)sf->names.size();
+                sf->names.emplace_back(p, nl);
+            }
+            sf->chrom.push_back(last_id = id);
+        }
+        p = t + 1;
+        // start, end
+        int64_t se[2] = {0, 0};
+        for (int f = 0; f < 2; ++f) {
+            long long v = 0;
+            bool negv = false;
+            if (p < e && *p == '-') {
+                negv = true;
+                ++p;
+            }
+            const char* d0 = p;
+            while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (*p++ - '0');
+            EPI_REQUIRE(p > d0 && p < e && *p == '\t', "%s: row %lld: bad coordinate field", path, (long long)r);
+            ++p;
+            se[f] = negv ? -v : v;
+        }
+        sf->starts.push_back(se[0]);
+        sf->ends.push_back(se[1]);
+        // scores
+        for (int j = 0; j < sf->cols; ++j) {
+            EPI_REQUIRE(p <= e, "%s: row %lld has %d score columns, expected %d", path, (long long)r, j, sf->cols);
+            const char* fe = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
+            if (fe == nullptr) fe = e;
+            EPI_REQUIRE(j == sf->cols - 1 || fe < e, "%s: row %lld has %d score columns, expected %d", path, (long long)r,
+                        j + 1, sf->cols);
+            EPI_REQUIRE(parse_decimal(p, fe, dst + j), "%s: row %lld column %d: not a number", path, (long long)r, j + 4);
+            p = fe + 1;
+        }
+        EPI_REQUIRE(p == e + 1, "%s: row %lld has more than %d score columns", path, (long long)r, sf->cols);
+        ++sf->rows;
+    }
+    size_t nb = 0;
+    for (const std::string& s : sf->names) nb += s.size() + 1;
+    if (rows_out) *rows_out = sf->rows;
+    if (cols_out) *cols_out = sf->cols;
+    if (n_chrom_out) *n_chrom_out = (int32_t)sf->names.size();
+    if (names_bytes_out) *names_bytes_out = (int32_t)nb;
+    *handle_out = sf.release();
+    return 0;
+}
+
+extern "C" int epi_scores_tsv_fetch(void* handle, double* scores, int64_t* starts, int64_t* ends, int32_t* chrom_id,
+                                    char* chrom_names, int32_t chrom_names_cap) {
+    ScoreFile* sf = static_cast<ScoreFile*>(handle);
+    EPI_REQUIRE(sf != nullptr, "null handle");
+    if (scores)
+        for (int64_t r0 = 0; r0 < sf->rows; r0 += ScoreFile::CHUNK_ROWS) {
+            const int64_t n = std::min<int64_t>(ScoreFile::CHUNK_ROWS, sf->rows - r0);
+            memcpy(scores + r0 * sf->cols, sf->vals[(size_t)(r0 / ScoreFile::CHUNK_ROWS)].data(),
+                   (size_t)n * sf->cols * sizeof(double));
+        }
+    const size_t n = (size_t)sf->rows;
+    if (starts && n) memcpy(starts, sf->starts.data(), n * sizeof(int64_t));
+    if (ends && n) memcpy(ends, sf->ends.data(), n * sizeof(int64_t));
+    if (chrom_id && n) memcpy(chrom_id, sf->chrom.data(), n * sizeof(int32_t));
+    return emit_names(sf->names, chrom_names, chrom_names_cap);
+}
+
+extern "C" int epi_scores_tsv_close(void* handle) {
+    delete static_cast<ScoreFile*>(handle);
     return 0;
 }
 

@@ -142,7 +142,8 @@ extern "C" int epi_roi_maxmean(const double* score, const int64_t* starts, const
         sorted_upto = want;
         want = std::min<int64_t>(p, want * 4);
     }
-    // ---- back to input order, then helpers.maxMean's final ranking by (RollingMax, RollingMean) descending ----
+    // ---- back to input order, then helpers.maxMean's final stable ranking by (RollingMax, RollingMean, Score) descending;
+    //      Score was overwritten with RollingMax by the 'max' aggregation (filter_regions.py:215-216), so two keys suffice ----
     std::sort(chosen.begin(), chosen.end());
     std::stable_sort(chosen.begin(), chosen.end(), [&](int64_t a, int64_t b) {
         const Cand &x = cand[(size_t)a], &y = cand[(size_t)b];

@@ -124,6 +124,33 @@ def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=Fal
     return loc, states0
 
 
+def read_scores(path):
+    """Parse a score file `chr start end score_1 .. score_K` (scores_*.txt.gz) with the native reader:
+    returns (locations dict as read_matrix, float64 [rows, K] scores).  Replaces the pandas read of
+    similaritySearch_max_mean.readScores (similaritySearch_max_mean.py:51-74); decimal text converts to the nearest
+    double, which is what pandas' parser yields for these files."""
+    path = Path(path)
+    if not path.is_file():
+        raise FileNotFoundError(str(path))
+    handle = ctypes.c_void_p(0)
+    rows_c, cols_c = ctypes.c_int64(0), ctypes.c_int32(0)
+    nnames, nbytes = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.call("epi_scores_tsv_open", str(path).encode(), ctypes.byref(handle), ctypes.byref(rows_c), ctypes.byref(cols_c),
+              ctypes.byref(nnames), ctypes.byref(nbytes))
+    try:
+        n, k = rows_c.value, max(cols_c.value, 0)
+        scores = np.empty((n, k), dtype=np.float64)
+        starts = np.empty(n, dtype=np.int64)
+        ends = np.empty(n, dtype=np.int64)
+        cid = np.empty(n, dtype=np.int32)
+        names = ctypes.create_string_buffer(max(nbytes.value, 1))
+        _lib.call("epi_scores_tsv_fetch", handle, ctypes.c_void_p(scores.ctypes.data), ctypes.c_void_p(starts.ctypes.data),
+                  ctypes.c_void_p(ends.ctypes.data), ctypes.c_void_p(cid.ctypes.data), names, len(names))
+    finally:
+        _lib.call("epi_scores_tsv_close", handle)
+    return _locations(names.raw, nnames.value, cid, starts, ends, n), scores
+
+
 def sharedToNumpy(sharedArr, numRows, numStates):
     """Kept for signature compatibility (helpers.py:315-327): view a flat float32 buffer as [rows, K]."""
     return np.frombuffer(sharedArr, dtype=np.float32).reshape((numRows, numStates))

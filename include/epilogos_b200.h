@@ -180,6 +180,16 @@ int epi_tsv_parse_close(void* handle);
 int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states, int8_t* out,
                  int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id, char* chrom_names,
                  int32_t chrom_names_cap, int32_t* n_chrom_out);
+/* Score text (`chr start end score_1 .. score_K`, what epi_write_scores_gz / scores.writeScores produce) back into
+ * float64 rows: replaces the pandas read of similaritySearch_max_mean.readScores (similaritySearch_max_mean.py:51-74).
+ * One pass: open parses the whole file (rows, columns, chromosome-name bytes out), fetch copies scores [rows][cols],
+ * starts, ends, chromosome ids and the NUL-separated name table, close frees the handle.  Decimal fields convert to
+ * the nearest double. */
+int epi_scores_tsv_open(const char* path, void** handle_out, int64_t* rows_out, int32_t* cols_out, int32_t* n_chrom_out,
+                        int32_t* names_bytes_out);
+int epi_scores_tsv_fetch(void* handle, double* scores, int64_t* starts, int64_t* ends, int32_t* chrom_id,
+                         char* chrom_names, int32_t chrom_names_cap);
+int epi_scores_tsv_close(void* handle);
 int epi_write_scores_gz(const char* path, const char* chrom_names, const int32_t* chrom_id, const int64_t* starts,
                         const int64_t* ends, const float* scores, int64_t rows, int32_t num_states, int32_t level,
                         int32_t threads);

@@ -149,3 +149,25 @@ def run_simsearch(reduced_genome, roi_starts, window_bins, block_size, n_desired
     ssc._initEuclideanDistance(genome_coords, reduced_genome, roi_coords, roi_cube, out, window_bins, block_size, n_desired)
     ssc.runEuclideanDistance((0, len(roi_starts)))
     return out
+
+
+def run_simsearch_prep(scores_path, window_bins, block_size, window_bp, filter_state, filter_score):
+    """similaritySearch_max_mean.main (similaritySearch_max_mean.py:9-48) of the unmodified reference on a score file.
+    Returns dict(genome_scores, genome_coords, cube_scores, cube_coords, reduced_genome) = the contents of
+    genome_stats.npz, simsearch_cube.npz and reduced_genome.npy."""
+    import contextlib
+    import io
+    import warnings
+    _import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos import similaritySearch_max_mean as mm
+        with tempfile.TemporaryDirectory() as tmp:
+            out = Path(tmp)
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                mm.main(out, Path(scores_path), int(window_bins), int(block_size), int(window_bp), int(filter_state),
+                        float(filter_score))
+            stats = np.load(out / "genome_stats.npz", allow_pickle=True)
+            cube = np.load(out / "simsearch_cube.npz", allow_pickle=True)
+            return dict(genome_scores=stats["scores"], genome_coords=stats["coords"], cube_scores=cube["scores"],
+                        cube_coords=cube["coords"], reduced_genome=np.load(out / "reduced_genome.npy", allow_pickle=True))

@@ -65,3 +65,66 @@ def similar_regions(reduced_genome, roi, region_start, n_desired):
         if found >= n_desired:
             break
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# preparation stage: similaritySearch_max_mean.py (window slices, filters, genome reduction)
+# ------------------------------------------------------------------------------------------------
+
+def row_sums(scores):
+    """DataFrame.sum(axis=1) of the score frame (similaritySearch_max_mean.py:67, 97, 152): pandas adds the state
+    columns one after another (checked against the reference: equal to the left-to-right sum, not to numpy's pairwise
+    sum of a contiguous row)."""
+    scores = np.asarray(scores, dtype=np.float64)
+    out = np.zeros(len(scores), dtype=np.float64)
+    for b in range(len(scores)):
+        acc = 0.0
+        for v in scores[b]:
+            acc = acc + v
+        out[b] = acc
+    return out
+
+
+def make_slice(scores, sums, idx, window_bins, block_size):
+    """makeSlice (similaritySearch_max_mean.py:77-98): rows [idx - w//2, idx + w//2 (+1 if w odd)), grouped by position
+    // blockSize, the first row with the largest sum of each group (groupby.idxmax)."""
+    lo = idx - window_bins // 2
+    hi = idx + window_bins // 2 + (1 if window_bins % 2 else 0)
+    keep = []
+    for g0 in range(lo, hi, block_size):
+        best = g0
+        for r in range(g0, min(g0 + block_size, hi)):
+            if sums[r] > sums[best]:
+                best = r
+        keep.append(best)
+    return np.asarray(scores)[keep]
+
+
+def remove_regions(coords, cube, filter_state, filter_score):
+    """removeRegions (similaritySearch_max_mean.py:101-134)."""
+    keep = []
+    for r in range(len(cube)):
+        if int(coords[r][1]) >= int(coords[r][2]):
+            continue
+        if filter_state != 0:
+            fs = cube.shape[2] - 1 if filter_state == -1 else filter_state - 1
+            if int(np.argmax(cube[r].max(axis=0))) == fs:
+                continue
+        if filter_score != -1 and cube[r].max() < filter_score:
+            continue
+        keep.append(r)
+    return [coords[r] for r in keep], cube[keep]
+
+
+def reduce_genome(scores, sums, block_size):
+    """reduceGenome (similaritySearch_max_mean.py:137-160): of every block of blockSize consecutive bins the one with the
+    largest sum (sort by sum, drop_duplicates(keep='last')).  The reference's sort is unstable, so WHICH of several bins
+    with exactly equal sums survives is not defined by the algorithm; this restatement takes the last one."""
+    keep = []
+    for g0 in range(0, len(scores), block_size):
+        best = g0
+        for r in range(g0, min(g0 + block_size, len(scores))):
+            if sums[r] >= sums[best]:
+                best = r
+        keep.append(best)
+    return np.asarray(scores)[keep]

@@ -150,6 +150,53 @@ def simsearch_case():
     print("wrote simsearch_g5000_k15_2chrom", out[:, :4].tolist(), (out == -1).sum(axis=1).tolist())
 
 
+def simsearch_prep_case():
+    """similaritySearch_max_mean.main of the reference on S1 scores of REAL data (60,000 bins of chr1, 10 biosamples,
+    long quiescent stretches = many exactly tied sums) and, with other window / filter settings, on a two-chromosome
+    synthetic track.  The fixture keeps the scores as integers (value x 1e5: exactly what the 5-decimal text holds)."""
+    import tempfile
+    from oracle import simsearch_oracle as sso
+    def run(name, q, chrom, starts, cfgs):
+        text = "".join("%s\t%d\t%d\t%s\n" % (chrom[i], starts[i], starts[i] + 200, "\t".join("%.5f" % (v / 1e5) for v in q[i]))
+                       for i in range(len(q)))
+        save = dict(scores_q=q, chrom=np.array(chrom), starts=np.asarray(starts, dtype=np.int64))
+        with tempfile.TemporaryDirectory() as tmp:
+            path = Path(tmp) / "scores_x.txt.gz"
+            with gzip.open(path, "wt", compresslevel=1) as f:
+                f.write(text)
+            for j, (wb, bs, wbp, fst, fsc) in enumerate(cfgs):
+                r = ref.run_simsearch_prep(path, wb, bs, wbp, fst, fsc)
+                assert np.array_equal(r["genome_scores"], q / 1e5)
+                # the restatement against the reference, here, before the fixture is trusted
+                sc = r["genome_scores"]
+                sums = sso.row_sums(sc)
+                assert np.array_equal(sso.reduce_genome(sc, sums, bs), r["reduced_genome"]), "reduce_genome restatement"
+                save["cfg%d" % j] = np.array([wb, bs, wbp, fst], dtype=np.int64)
+                save["filter_score%d" % j] = np.float64(fsc)
+                save["cube_chrom%d" % j] = np.array([str(c) for c in r["cube_coords"][:, 0]])
+                save["cube_start%d" % j] = r["cube_coords"][:, 1].astype(np.int64)
+                save["cube_end%d" % j] = r["cube_coords"][:, 2].astype(np.int64)
+                save["cube_digest%d" % j] = text_digest(np.ascontiguousarray(r["cube_scores"]).tobytes())
+                save["cube_shape%d" % j] = np.array(r["cube_scores"].shape, dtype=np.int64)
+                save["cube_first%d" % j] = r["cube_scores"][:3]
+                save["reduced_digest%d" % j] = text_digest(np.ascontiguousarray(r["reduced_genome"]).tobytes())
+                save["reduced_rows%d" % j] = np.int64(len(r["reduced_genome"]))
+                print(name, "cfg", j, "regions", r["cube_scores"].shape, "reduced", r["reduced_genome"].shape)
+        save["n_cfg"] = np.int64(len(cfgs))
+        np.savez_compressed(HERE / (name + ".npz"), **save)
+    x = real_slice(lo=100000, n=60000)
+    _, sc32 = orc.expected_and_scores(x, 18, 1)
+    q = np.round(sc32.astype(np.float64) * 1e5).astype(np.int32)
+    run("simsearch_prep_real_chr1_60k", q, ["chr1"] * len(q), (100000 + np.arange(len(q))) * 200,
+        [(125, 5, 25000, -1, -1.0), (50, 2, 10000, 0, 1.5)])
+    rng = np.random.default_rng(5)
+    b, k = 9003, 15                                         # not a multiple of the block size: a partial last block
+    q = (np.round(rng.gamma(0.3, 1.0, (b, k)) * (rng.random((b, 1)) < 0.3), 5) * 1e5).astype(np.int32)
+    chrom = ["chr1"] * 5000 + ["chrX"] * (b - 5000)
+    starts = np.concatenate((np.arange(5000), np.arange(b - 5000))) * 200
+    run("simsearch_prep_synth_2chrom", q, chrom, starts, [(125, 5, 25000, -1, -1.0), (25, 1, 5000, 3, 2.0), (500, 20, 100000, 0, -1.0)])
+
+
 def roi_cases():
     """helpers.maxMean of the reference (the ROI selector that consumes the single-mode scores) on
     (a) S1 scores of a 200 000-bin real-data slice, window 50, and (b) two short synthetic chromosomes with odd /
@@ -226,6 +273,8 @@ def main():
         real_full_case()
     if want("simsearch"):
         simsearch_case()
+    if want("simsearch_prep"):
+        simsearch_prep_case()
 
 
 if __name__ == "__main__":
