@@ -44,6 +44,17 @@ def gather_rows(t, total_rows, dst=0):
     return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0)
 
 
+def init_from_env():
+    """Join the NCCL process group when launched by torchrun (RANK / WORLD_SIZE / LOCAL_RANK in the environment):
+    one process per GPU, pinned to the GPU's NUMA node.  A plain `python` launch stays single-rank."""
+    import os
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ and not initialised():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        bind_to_gpu_numa(local)
+        dist.init_process_group("nccl")
+
+
 def barrier():
     if initialised():
         dist.barrier()

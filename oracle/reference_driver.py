@@ -171,3 +171,57 @@ def run_simsearch_prep(scores_path, window_bins, block_size, window_bp, filter_s
             cube = np.load(out / "simsearch_cube.npz", allow_pickle=True)
             return dict(genome_scores=stats["scores"], genome_coords=stats["coords"], cube_scores=cube["scores"],
                         cube_coords=cube["coords"], reduced_genome=np.load(out / "reduced_genome.npy", allow_pickle=True))
+
+
+def run_simsearch_build(scores_path, window_bins, block_size, window_bp, filter_state, filter_score, n_desired, n_jobs=1):
+    """The reference's whole `simsearch -b` chain without SLURM: similaritySearch_max_mean.main ->
+    similaritySearch_calc.main (one call per job, nCores = 1) -> similaritySearch_write.main.
+    pysam is absent from this image and the writer puts its temporary file into the (read-only) reference tree, so two
+    stand-ins are installed around the UNMODIFIED writer code: `pysam.tabix_compress` = a plain gzip copy and
+    `pysam.tabix_index` = a placeholder file; `tempfile` is redirected to the output directory.  The bed TEXT is the
+    reference's own.  Returns dict(indices int32 [regions, n_desired], bed_text bytes, cube_coords, cube_scores,
+    reduced_genome)."""
+    import contextlib
+    import gzip
+    import io
+    import shutil
+    import warnings
+    _import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from epilogos import similaritySearch_max_mean as mm
+        from epilogos import similaritySearch_calc as ssc
+        from epilogos import similaritySearch_write as ssw
+        with tempfile.TemporaryDirectory() as tmp:
+            out = Path(tmp) / "out"
+            out.mkdir()
+
+            def tabix_compress(src, dst, force=False):
+                with open(src, "rb") as a, gzip.open(dst, "wb") as b:
+                    shutil.copyfileobj(a, b)
+
+            def tabix_index(fn, force=False, zerobased=False, preset=None):
+                Path(str(fn) + ".tbi").write_bytes(b"placeholder")
+
+            class _Tempfile:
+                @staticmethod
+                def NamedTemporaryFile(mode="w+b", delete=True, dir=None):
+                    return tempfile.NamedTemporaryFile(mode=mode, delete=delete, dir=tmp)
+
+            ssw.pysam.tabix_compress = tabix_compress
+            ssw.pysam.tabix_index = tabix_index
+            ssw.tempfile = _Tempfile
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                mm.main(out, Path(scores_path), int(window_bins), int(block_size), int(window_bp), int(filter_state),
+                        float(filter_score))
+                cube = np.load(out / "simsearch_cube.npz", allow_pickle=True)
+                cube_scores, cube_coords = cube["scores"], cube["coords"]
+                reduced = np.load(out / "reduced_genome.npy", allow_pickle=True)
+                for tag in range(n_jobs):
+                    ssc.main(out, int(window_bins), int(block_size), 1, int(n_desired), int(n_jobs), tag)
+                ssw.main(out, int(window_bins), int(block_size), int(n_jobs), int(n_desired))
+            with gzip.open(out / "simsearch.bed.gz", "rb") as f:
+                bed = f.read()
+            return dict(indices=np.load(out / "simsearch_indices.npy", allow_pickle=True), bed_text=bed,
+                        cube_coords=cube_coords, cube_scores=cube_scores, reduced_genome=reduced,
+                        leftovers=sorted(p.name for p in out.iterdir()))

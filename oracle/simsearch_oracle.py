@@ -128,3 +128,27 @@ def reduce_genome(scores, sums, block_size):
                 best = r
         keep.append(best)
     return np.asarray(scores)[keep]
+
+
+# ------------------------------------------------------------------------------------------------
+# output stage: similaritySearch_write.py (indices -> coordinates -> bed text)
+# ------------------------------------------------------------------------------------------------
+
+def bed_text(indices, genome_coords, roi_coords, window_bins, block_size):
+    """The uncompressed text of simsearch.bed.gz (similaritySearch_write.py:44-67 reduced coordinates, :95-124 index ->
+    coordinates, :142-152 one JSON list per region with the region itself first, sorted by (chrom, start))."""
+    import json
+    n = len(genome_coords)
+    n_super = window_bins // block_size
+    rows = []
+    for r in range(len(indices)):
+        recs = ["%s:%s:%s" % (roi_coords[r][0], roi_coords[r][1], roi_coords[r][2])]
+        for w in indices[r]:
+            if w == -1:
+                continue
+            first = int(w) * block_size
+            last = min((int(w) + n_super - 1) * block_size + block_size - 1, n - 1)
+            recs.append("%s:%s:%s" % (genome_coords[first][0], genome_coords[first][1], genome_coords[last][2]))
+        rows.append((roi_coords[r][0], roi_coords[r][1], roi_coords[r][2], json.dumps(recs)))
+    rows.sort(key=lambda t: (t[0], t[1]))
+    return "".join("%s\t%s\t%s\t%s\n" % t for t in rows).encode()

@@ -197,6 +197,38 @@ def simsearch_prep_case():
     run("simsearch_prep_synth_2chrom", q, chrom, starts, [(125, 5, 25000, -1, -1.0), (25, 1, 5000, 3, 2.0), (500, 20, 100000, 0, -1.0)])
 
 
+def simsearch_chain_case():
+    """The reference's whole `simsearch -b` chain (max_mean -> calc -> write, oracle/reference_driver.run_simsearch_build)
+    on the real-data scores of the simsearch_prep fixture: the index array, the bed text and, checked here, the oracle's
+    restatement of the picks and of the text."""
+    import tempfile
+    from oracle import simsearch_oracle as sso
+    g = np.load(HERE / "simsearch_prep_real_chr1_60k.npz")
+    q, chrom, starts = g["scores_q"], g["chrom"], g["starts"]
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "scores_x.txt.gz"
+        with gzip.open(path, "wt", compresslevel=1) as f:
+            f.write("".join("%s\t%d\t%d\t%s\n" % (chrom[i], starts[i], starts[i] + 200, "\t".join("%.5f" % (v / 1e5) for v in q[i]))
+                            for i in range(len(q))))
+        r = ref.run_simsearch_build(path, 125, 5, 25000, -1, -1.0, 100, n_jobs=3)
+    idx = r["indices"]
+    print("chain: regions", idx.shape, "matches per region (min/median/max)", [(int(f((idx > 0).sum(axis=1)))) for f in (np.min, np.median, np.max)],
+          "leftovers", r["leftovers"])
+    # oracle restatements against the reference, before the fixture is trusted
+    coords = np.empty((len(q), 3), dtype=object)
+    coords[:, 0], coords[:, 1], coords[:, 2] = chrom, starts.tolist(), (starts + 200).tolist()
+    assert sso.bed_text(idx, coords, r["cube_coords"], 125, 5) == r["bed_text"], "bed text restatement"
+    mism = 0
+    for i in range(len(idx)):
+        s0 = int(np.flatnonzero(starts == r["cube_coords"][i][1])[0]) // 5
+        got = sso.similar_regions(r["reduced_genome"], r["cube_scores"][i], s0, 100)
+        mism += int(not np.array_equal(got, idx[i]))
+    print("chain: oracle picks differ from the reference for", mism, "of", len(idx), "regions (exact distance ties)")
+    np.savez_compressed(HERE / "simsearch_chain_real_chr1_60k.npz", indices=idx, bed_digest=text_digest(r["bed_text"]),
+                        bed_head=np.frombuffer(r["bed_text"][:2000], dtype=np.uint8), bed_bytes=np.int64(len(r["bed_text"])),
+                        leftovers=np.array(r["leftovers"]), oracle_mismatches=np.int64(mism))
+
+
 def roi_cases():
     """helpers.maxMean of the reference (the ROI selector that consumes the single-mode scores) on
     (a) S1 scores of a 200 000-bin real-data slice, window 50, and (b) two short synthetic chromosomes with odd /
@@ -275,6 +307,8 @@ def main():
         simsearch_case()
     if want("simsearch_prep"):
         simsearch_prep_case()
+    if want("simsearch_chain"):
+        simsearch_chain_case()
 
 
 if __name__ == "__main__":

@@ -80,3 +80,27 @@ def test_mode_of_sorted_edge_cases():
                      [0.0, 1.0, 1.0, 1.0, 7.0, 7.0, 7.0, 7.0]])         # the longer run at the end
     got = ssc.mode_of_sorted(torch.from_numpy(rows).cuda()).cpu().numpy()
     assert got.tolist() == [1.0, 0.5, 2.0, 7.0]
+
+
+def test_whole_build_chain_on_real_scores_matches_reference(golden, tmp_path):
+    """`simsearch -b` end to end (score text -> max-mean regions -> GPU distance engine -> bed file) on S1 scores of 60,000
+    real chr1 bins: the index array and the bed text of the unmodified reference's chain (358 regions x 100 matches)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import gzip
+    import hashlib
+    from test_simsearch_prep import _write_scores
+    from epilogos_b200 import similaritySearch_run as ssr
+    c = golden("simsearch_chain_real_chr1_60k")
+    path = tmp_path / "scores_x.txt.gz"
+    _write_scores(path, golden("simsearch_prep_real_chr1_60k"))
+    out = tmp_path / "build"
+    out.mkdir()
+    idx = ssr.buildSimSearch(path, out, -1, 100, -1, -1.0)
+    assert idx.dtype == np.int32 and idx.shape == c["indices"].shape
+    bad = np.flatnonzero((idx != c["indices"]).any(axis=1))
+    assert len(bad) == 0, "regions with different picks: %s" % bad[:10]
+    with gzip.open(out / "simsearch.bed.gz", "rb") as f:
+        text = f.read()
+    assert np.array_equal(np.frombuffer(hashlib.sha256(text).digest(), dtype=np.uint8), c["bed_digest"])
+    assert not (out / "genome_stats.npz").exists() and not list(out.glob("simsearch_indices_*.npy"))

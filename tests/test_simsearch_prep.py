@@ -98,3 +98,79 @@ def test_score_reader_fields_and_errors(tmp_path):
         helpers.read_scores(bad)
     with pytest.raises(FileNotFoundError):
         helpers.read_scores(tmp_path / "missing.txt")
+
+
+def _prepared(tmp_path, golden):
+    from epilogos_b200 import similaritySearch_max_mean as mm
+    g = golden("simsearch_prep_real_chr1_60k")
+    path = tmp_path / "scores_x.txt.gz"
+    _write_scores(path, g)
+    out = tmp_path / "build"
+    out.mkdir()
+    mm.main(out, path, 125, 5, 25000, -1, -1.0)
+    return path, out
+
+
+def test_write_stage_matches_reference_text(tmp_path, golden):
+    """similaritySearch_write.main on the reference's own index array (split over three job files, as its SLURM jobs
+    leave them): same bed text, same files left behind, and a well-formed BGZF container."""
+    import struct
+    from epilogos_b200 import similaritySearch_write as ssw
+    from epilogos_b200.helpers import splitRows
+    c = golden("simsearch_chain_real_chr1_60k")
+    _, out = _prepared(tmp_path, golden)
+    idx = c["indices"]
+    for j, (lo, hi) in enumerate(splitRows(len(idx), 3)):
+        np.save(out / ("simsearch_indices_%d.npy" % j), idx[lo:hi])
+    ssw.main(out, 125, 5, 3, idx.shape[1])
+    with gzip.open(out / "simsearch.bed.gz", "rb") as f:
+        text = f.read()
+    assert len(text) == int(c["bed_bytes"]) and text[:2000] == c["bed_head"].tobytes()
+    assert np.array_equal(np.frombuffer(hashlib.sha256(text).digest(), dtype=np.uint8), c["bed_digest"])
+    assert np.array_equal(np.load(out / "simsearch_indices.npy"), idx)
+    left = sorted(p.name for p in out.iterdir())
+    assert left == [n for n in c["leftovers"] if not n.endswith(".tbi")]           # the tabix index is not produced here
+    # BGZF: every member carries the BC extra field with its own size, the file ends with the empty EOF member
+    raw = (out / "simsearch.bed.gz").read_bytes()
+    off, blocks = 0, 0
+    while off < len(raw):
+        assert raw[off:off + 4] == b"\x1f\x8b\x08\x04" and raw[off + 12:off + 16] == b"BC\x02\x00"
+        off += struct.unpack_from("<H", raw, off + 16)[0] + 1
+        blocks += 1
+    assert off == len(raw) and blocks >= 2 and raw[-28:] == ssw._BGZF_EOF
+    # the oracle's restatement of the text from the same inputs
+    cube = np.load(out / "simsearch_cube.npz", allow_pickle=True)
+    g = golden("simsearch_prep_real_chr1_60k")
+    coords = [(ch, int(s), int(s) + 200) for ch, s in zip(g["chrom"], g["starts"])]
+    assert sso.bed_text(idx, coords, cube["coords"], 125, 5) == text
+
+
+def test_query_mode_and_cli_validation(tmp_path, golden):
+    from click.testing import CliRunner
+    from epilogos_b200 import similaritySearch_run as ssr, similaritySearch_write as ssw
+    lines = ('chr1\t1000\t26000\t["chr1:1000:26000", "chr2:5000:30000", "chrX:0:25000"]\n'
+             'chr1\t50000\t75000\t["chr1:50000:75000"]\n'
+             'chr2\t0\t25000\t["chr2:0:25000", "chr1:1000:26000"]\n')
+    bed = tmp_path / "simsearch.bed.gz"
+    ssw.bgzf_write(bed, lines.encode())
+    qdir = tmp_path / "q"
+    res = CliRunner().invoke(ssr.main, ["-q", "chr1:0-30000", "-m", str(bed), "-o", str(qdir)])
+    assert res.exit_code == 0, res.output
+    assert (qdir / "similarity_search_region_chr1_1000_26000_recs.bed").read_text() == "chr2\t5000\t30000\nchrX\t0\t25000\n"
+    qfile = tmp_path / "queries.bed"
+    qfile.write_text("chr1\t40000\t80000\nchr2\t0\t26000\nchr9\t0\t10\n")
+    written = ssr.querySimSearch(str(qfile), bed, qdir)
+    assert [w.name for w in written] == ["similarity_search_region_chr1_50000_75000_recs.bed",
+                                         "similarity_search_region_chr2_0_25000_recs.bed"]
+    assert written[0].read_text() == "" and written[1].read_text() == "chr1\t1000\t26000\n"
+    with pytest.raises(ValueError, match="valid query"):
+        ssr.generateRegionArr("1:5-9")
+    for args, msg in ((["-o", str(qdir)], "Either -b or -q"), (["-b", "-q", "chr1:1-2", "-o", str(qdir)], "Both -b and -q")):
+        res = CliRunner().invoke(ssr.main, args)
+        assert isinstance(res.exception, ValueError) and msg in str(res.exception)
+    assert ssr.determineBlockSize200(25000) == 5 and ssr.determineBlockSize20(10000) == 20
+    with pytest.raises(ValueError, match="window size"):
+        ssr.determineBlockSize200(30000)
+    p = tmp_path / "s.txt"
+    p.write_text("chr1\t400\t600\t0.1\n")
+    assert ssr.determineBinSize(p) == 200
