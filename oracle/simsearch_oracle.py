@@ -42,10 +42,14 @@ def float_mode(values):
     return u[np.argmax(c)]
 
 
-def similar_regions(reduced_genome, roi, region_start, n_desired):
+def similar_regions(reduced_genome, roi, region_start, n_desired, tie_order="numpy", return_distances=False):
     """similaritySearch_calc.py:101-123 for one ROI whose own window starts at reduced bin `region_start`.
     Returns int32 [n_desired] (unused slots keep 0 when the list ends by exhaustion, -1 after a threshold stop -- the
-    reference pre-fills its output array with zeros and writes -1 only on the threshold branch)."""
+    reference pre-fills its output array with zeros and writes -1 only on the threshold branch).
+    tie_order: windows at exactly equal distance are visited in the order of numpy's default (unstable, platform
+    dependent) argsort, as the reference does ("numpy"), or in ascending window index ("index": what a stable sort gives
+    and what the GPU engine does).  On real tracks adjacent windows of a repeated pattern tie exactly, so the two orders
+    pick different members of a tie now and then; the distances of the picks are the same."""
     d = window_distances(reduced_genome, roi)
     n_super = np.asarray(roi).shape[0]
     half_mode = float_mode(d) / 2
@@ -53,7 +57,7 @@ def similar_regions(reduced_genome, roi, region_start, n_desired):
     overlap[region_start:region_start + n_super] = 1
     out = np.zeros(n_desired, dtype=np.int32)
     found = 0
-    for hit in np.argsort(d):
+    for hit in (np.argsort(d) if tie_order == "numpy" else np.argsort(d, kind="stable")):
         if np.any(overlap[hit:hit + n_super]):
             continue
         if d[hit] > half_mode:
@@ -64,7 +68,7 @@ def similar_regions(reduced_genome, roi, region_start, n_desired):
         found += 1
         if found >= n_desired:
             break
-    return out
+    return (out, d) if return_distances else out
 
 
 # ------------------------------------------------------------------------------------------------

