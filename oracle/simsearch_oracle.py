@@ -5,8 +5,11 @@ Reference: similaritySearch_calc.runEuclideanDistance (similaritySearch_calc.py:
 every window of the reduced genome, takes half the MODE of those distances as the acceptance threshold, and greedily
 picks up to nDesiredMatches non-overlapping windows in increasing distance (never the ROI itself).
 
-No product code exists for this row yet; this restatement and its golden fixture
-(tests/golden/simsearch_*.npz, produced by the unmodified reference) are the parity anchor for the kernel to come.
+Also restated: the preparation stage (similaritySearch_max_mean.py: window slices, region filters, genome reduction) and
+the text of the output stage (similaritySearch_write.py).  The product code (csrc/simsearch.cu, csrc/hostio.cu and the
+epilogos_b200.similaritySearch_* modules) never imports this file; the restatement and its fixtures
+(tests/golden/simsearch_*.npz, produced by the unmodified reference through oracle/reference_driver.py) are the parity
+anchor: checked against reference output in tests/test_oracle_golden.py and tests/test_simsearch_prep.py.
 
 Parity notes found while pinning it:
   * the reference's distances come out of sklearn's euclidean_distances = XX + YY - 2 X.Y^T (a BLAS dgemm) clipped at 0,
