@@ -174,3 +174,43 @@ def test_query_mode_and_cli_validation(tmp_path, golden):
     p = tmp_path / "s.txt"
     p.write_text("chr1\t400\t600\t0.1\n")
     assert ssr.determineBinSize(p) == 200
+
+
+def test_build_driver_host_chain_with_oracle_engine(tmp_path, golden, monkeypatch):
+    """similaritySearch_run.buildSimSearch wiring on CPU: bin size -> window / block size, preparation, per-job index
+    files, writer, clean-up.  The GPU distance engine is replaced by the oracle's restatement of the reference's picks
+    (checker standing in for the one stage that needs a device), so everything else must reproduce the reference's index
+    array and bed text bit for bit."""
+    from epilogos_b200 import similaritySearch_calc, similaritySearch_run as ssr
+    from epilogos_b200.helpers import splitRows
+    prep = golden("simsearch_prep_real_chr1_60k")
+    c = golden("simsearch_chain_real_chr1_60k")
+    path = tmp_path / "scores_x.txt.gz"
+    _write_scores(path, prep)
+    out = tmp_path / "build"
+    calls = []
+
+    def oracle_engine(outputDir, windowBins, blockSize, nCores, nDesiredMatches, nJobs, processTag):
+        calls.append((windowBins, blockSize, nDesiredMatches, nJobs, processTag))
+        cube = np.load(outputDir / "simsearch_cube.npz", allow_pickle=True)
+        red = np.load(outputDir / "reduced_genome.npy")
+        lo, hi = splitRows(len(cube["scores"]), nJobs)[processTag]
+        res = np.zeros((hi - lo, nDesiredMatches), dtype=np.int32)
+        for r in range(lo, hi):
+            s0 = int(np.flatnonzero(prep["starts"] == cube["coords"][r][1])[0]) // blockSize
+            res[r - lo] = sso.similar_regions(red, cube["scores"][r], s0, nDesiredMatches)
+        np.save(outputDir / "simsearch_indices_{}.npy".format(processTag), res)
+
+    monkeypatch.setattr(similaritySearch_calc, "main", oracle_engine)
+    out.mkdir()
+    idx = ssr.buildSimSearch(path, out, -1, 100, -1, -1.0)
+    assert calls == [(125, 5, 100, 1, 0)]
+    assert np.array_equal(idx, c["indices"])
+    with gzip.open(out / "simsearch.bed.gz", "rb") as f:
+        text = f.read()
+    assert np.array_equal(np.frombuffer(hashlib.sha256(text).digest(), dtype=np.uint8), c["bed_digest"])
+    assert sorted(p.name for p in out.iterdir()) == [n for n in c["leftovers"] if not n.endswith(".tbi")]
+    bad = tmp_path / "bins50.txt"
+    bad.write_text("chr1\t0\t50\t0.1\n")
+    with pytest.raises(ValueError, match="200bp or 20bp"):
+        ssr.buildSimSearch(bad, out, -1, 100, -1, -1.0)
