@@ -1,6 +1,5 @@
 """`epilogos` command line mirror (epilogos_b200.run): flag validation on CPU, full local pipeline on the GPU."""
 import gzip
-from pathlib import Path
 
 import numpy as np
 import pytest
