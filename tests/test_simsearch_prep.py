@@ -214,3 +214,24 @@ def test_build_driver_host_chain_with_oracle_engine(tmp_path, golden, monkeypatc
     bad.write_text("chr1\t0\t50\t0.1\n")
     with pytest.raises(ValueError, match="200bp or 20bp"):
         ssr.buildSimSearch(bad, out, -1, 100, -1, -1.0)
+
+
+def test_score_reader_decimal_forms_equal_python_float(tmp_path):
+    """Every way a float can be written in a score file converts to the same double as Python's float(): fixed
+    notation with 0..20 decimals (the fast path up to 15 significant digits, strtod beyond), exponents, repr(), big
+    integers, leading zeros, an explicit plus sign."""
+    from epilogos_b200 import helpers
+    rng = np.random.default_rng(11)
+    texts = []
+    for v in np.concatenate((rng.normal(0, 1, 300), rng.normal(0, 1e4, 300), rng.uniform(-1e-6, 1e-6, 200),
+                             rng.integers(-10**15, 10**15, 100).astype(np.float64))):
+        v = float(v)
+        texts += ["%.*f" % (int(rng.integers(0, 21)), v), "%e" % v, "%.17g" % v, repr(v), "%.5f" % v]
+    texts += ["0", "-0", "+1.5", "000123.4500", "1.", ".5", "123456789012345", "1234567890123456", "9007199254740993",
+              "0.1234567890123456789", "12345678901234567890123", "1e22", "1E-7", "4.9e-324", "1.7976931348623157e308"]
+    p = tmp_path / "forms.txt"
+    p.write_text("".join("c\t%d\t%d\t%s\n" % (i, i + 1, t) for i, t in enumerate(texts)))
+    _, got = helpers.read_scores(p)
+    want = np.array([float(t) for t in texts])
+    bad = [(t, g, w) for t, g, w in zip(texts, got[:, 0], want) if not (g == w and np.signbit(g) == np.signbit(w))]
+    assert not bad, bad[:5]
