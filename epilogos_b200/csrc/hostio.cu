@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <memory>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -138,16 +140,20 @@ extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_
     return 0;
 }
 
-// Line source: a background thread inflates the file into a ring of large blocks while the caller parses the
-// previous one; lines that straddle a block boundary are stitched into a side buffer.
+// Line source: a background thread inflates the file into a ring of two large blocks while the caller parses the
+// previous one; lines that straddle a block boundary are stitched into a side buffer.  The two threads hand blocks over
+// through a mutex + condition variable (no spinning: with one reader per input file running concurrently, a spinning
+// parser would take the core its own inflate thread needs).
 struct LineSource {
     static constexpr size_t BLOCK = 16u << 20;
     gzFile gz = nullptr;
     std::vector<char> blocks[2];
     size_t lens[2] = {0, 0};
     std::thread worker;
-    std::atomic<int> ready[2];          // 1 = filled by the worker, 0 = free
-    std::atomic<bool> done{false};
+    std::mutex mu;
+    std::condition_variable cv;
+    int ready[2] = {0, 0};              // 1 = filled by the worker, 0 = free (guarded by mu)
+    bool abort_ = false;                // the reader is going away: stop inflating
     int cur = 0;
     size_t pos = 0;
     std::vector<char> carry;
@@ -158,29 +164,43 @@ struct LineSource {
         gzbuffer(gz, 1 << 20);
         blocks[0].resize(BLOCK);
         blocks[1].resize(BLOCK);
-        ready[0] = ready[1] = 0;
         worker = std::thread([this]() {
             int w = 0;
             for (;;) {
-                while (ready[w].load(std::memory_order_acquire) != 0) std::this_thread::yield();
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready[w] == 0 || abort_; });
+                    if (abort_) return;
+                }
                 const int n = gzread(gz, blocks[w].data(), (unsigned)BLOCK);
-                lens[w] = n > 0 ? (size_t)n : 0;
                 const bool last = n <= 0;
-                if (last) done.store(true, std::memory_order_release);
-                ready[w].store(1, std::memory_order_release);
-                if (last) break;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    lens[w] = n > 0 ? (size_t)n : 0;
+                    ready[w] = 1;
+                }
+                cv.notify_all();
+                if (last) return;
                 w ^= 1;
             }
         });
-        while (ready[0].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        wait_filled(0);
         return true;
+    }
+    void wait_filled(int b) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ready[b] == 1; });
     }
     // advance to the next block; false at end of file
     bool next_block() {
-        ready[cur].store(0, std::memory_order_release);
-        if (lens[cur] == 0) return false;
+        if (lens[cur] == 0) return false;          // the empty block marks the end of the stream: nothing follows it
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            ready[cur] = 0;
+        }
+        cv.notify_all();
         cur ^= 1;
-        while (ready[cur].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        wait_filled(cur);
         pos = 0;
         return lens[cur] != 0;
     }
@@ -225,13 +245,12 @@ struct LineSource {
     }
     std::vector<char> line_buf;
     ~LineSource() {
-        // let the worker finish: mark both blocks free until it reports the end of the stream
         if (worker.joinable()) {
-            while (!done.load(std::memory_order_acquire)) {
-                ready[0].store(0, std::memory_order_release);
-                ready[1].store(0, std::memory_order_release);
-                std::this_thread::yield();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                abort_ = true;
             }
+            cv.notify_all();
             worker.join();
         }
         if (gz) gzclose(gz);
