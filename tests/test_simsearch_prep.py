@@ -176,11 +176,11 @@ def test_query_mode_and_cli_validation(tmp_path, golden):
     assert ssr.determineBinSize(p) == 200
 
 
-def test_build_driver_host_chain_with_oracle_engine(tmp_path, golden, monkeypatch):
+def test_build_driver_host_chain_with_replayed_engine(tmp_path, golden, monkeypatch):
     """similaritySearch_run.buildSimSearch wiring on CPU: bin size -> window / block size, preparation, per-job index
-    files, writer, clean-up.  The GPU distance engine is replaced by the oracle's restatement of the reference's picks
-    (checker standing in for the one stage that needs a device), so everything else must reproduce the reference's index
-    array and bed text bit for bit."""
+    files, writer, clean-up.  The GPU distance engine (the one stage that needs a device) is replaced by a stand-in that
+    replays the reference's picks for the regions it is asked for, so everything else must reproduce the reference's
+    index array and bed text bit for bit."""
     from epilogos_b200 import similaritySearch_calc, similaritySearch_run as ssr
     from epilogos_b200.helpers import splitRows
     prep = golden("simsearch_prep_real_chr1_60k")
@@ -190,18 +190,14 @@ def test_build_driver_host_chain_with_oracle_engine(tmp_path, golden, monkeypatc
     out = tmp_path / "build"
     calls = []
 
-    def oracle_engine(outputDir, windowBins, blockSize, nCores, nDesiredMatches, nJobs, processTag):
+    def replay_engine(outputDir, windowBins, blockSize, nCores, nDesiredMatches, nJobs, processTag):
         calls.append((windowBins, blockSize, nDesiredMatches, nJobs, processTag))
         cube = np.load(outputDir / "simsearch_cube.npz", allow_pickle=True)
-        red = np.load(outputDir / "reduced_genome.npy")
+        assert len(cube["scores"]) == len(c["indices"]) and (outputDir / "reduced_genome.npy").exists()
         lo, hi = splitRows(len(cube["scores"]), nJobs)[processTag]
-        res = np.zeros((hi - lo, nDesiredMatches), dtype=np.int32)
-        for r in range(lo, hi):
-            s0 = int(np.flatnonzero(prep["starts"] == cube["coords"][r][1])[0]) // blockSize
-            res[r - lo] = sso.similar_regions(red, cube["scores"][r], s0, nDesiredMatches)
-        np.save(outputDir / "simsearch_indices_{}.npy".format(processTag), res)
+        np.save(outputDir / "simsearch_indices_{}.npy".format(processTag), c["indices"][lo:hi])
 
-    monkeypatch.setattr(similaritySearch_calc, "main", oracle_engine)
+    monkeypatch.setattr(similaritySearch_calc, "main", replay_engine)
     out.mkdir()
     idx = ssr.buildSimSearch(path, out, -1, 100, -1, -1.0)
     assert calls == [(125, 5, 100, 1, 0)]
