@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fast_inflate.h"
 
 namespace epi {
 
@@ -146,8 +147,9 @@ extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_
 // parser would take the core its own inflate thread needs).
 struct LineSource {
     static constexpr size_t BLOCK = 16u << 20;
+    static constexpr size_t HIST = 32768;       // DEFLATE window kept in front of every block for the native decoder
     gzFile gz = nullptr;
-    std::vector<char> blocks[2];
+    std::vector<char> blocks[2];                // [HIST bytes of history | BLOCK bytes of text | slack]
     size_t lens[2] = {0, 0};
     std::thread worker;
     std::mutex mu;
@@ -157,35 +159,149 @@ struct LineSource {
     int cur = 0;
     size_t pos = 0;
     std::vector<char> carry;
+    std::string path_;
+    std::string error_;                 // set by the worker before its last block is published
+    std::vector<uint8_t> packed;        // the whole compressed file (native decoder)
+    FastInflate inflater;
+    bool native = false;
+    uint64_t delivered = 0;             // bytes handed to the parser in complete blocks
+
+    char* text(int w) { return blocks[w].data() + HIST; }
+
+    // the whole file in memory if it is gzip and the native decoder is not disabled (EPI_ZLIB_INFLATE=1)
+    bool load_packed(const char* path) {
+        if (getenv("EPI_ZLIB_INFLATE") != nullptr) return false;
+        FILE* f = fopen(path, "rb");
+        if (!f) return false;
+        unsigned char magic[2] = {0, 0};
+        const bool gzip = fread(magic, 1, 2, f) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        bool ok = false;
+        if (gzip && fseek(f, 0, SEEK_END) == 0) {
+            const long long size = ftell(f);
+            if (size > 0 && fseek(f, 0, SEEK_SET) == 0) {
+                packed.assign((size_t)size + 16, 0);
+                ok = fread(packed.data(), 1, (size_t)size, f) == (size_t)size;
+            }
+        }
+        fclose(f);
+        if (!ok) std::vector<uint8_t>().swap(packed);
+        return ok;
+    }
+
+    // fill block w with the native decoder; returns the bytes produced (BLOCK unless the stream ended) or -1 on error
+    long long fill_native(int w, uint32_t& crc, uint64_t& member_bytes) {
+        uint8_t* base = reinterpret_cast<uint8_t*>(text(w));
+        uint8_t* out = base;
+        uint8_t* const end = base + BLOCK;
+        while (out < end) {
+            if (inflater.at_end_of_input()) break;
+            uint8_t* np = out;
+            const FastInflate::Status st = inflater.decode(out, end, &np);
+            crc = (uint32_t)crc32(crc, out, (uInt)(np - out));
+            member_bytes += (uint64_t)(np - out);
+            out = np;
+            if (st == FastInflate::ERROR) return -1;
+            if (st == FastInflate::MEMBER_END) {
+                if (crc != inflater.member_crc() || (uint32_t)member_bytes != inflater.member_isize()) {
+                    error_ = path_ + ": gzip member fails its CRC-32 / length check";
+                    return -2;
+                }
+                crc = (uint32_t)crc32(0L, Z_NULL, 0);
+                member_bytes = 0;
+                if (inflater.only_padding_left()) break;
+            }
+        }
+        return (long long)(out - base);
+    }
 
     bool open(const char* path) {
-        gz = gzopen(path, "rb");
-        if (!gz) return false;
-        gzbuffer(gz, 1 << 20);
-        blocks[0].resize(BLOCK);
-        blocks[1].resize(BLOCK);
+        path_ = path;
+        native = load_packed(path);
+        if (!native) {
+            gz = gzopen(path, "rb");
+            if (!gz) return false;
+            gzbuffer(gz, 1 << 20);
+        } else {
+            inflater.reset(packed.data(), packed.size() - 16);
+        }
+        blocks[0].resize(HIST + BLOCK + 64);
+        blocks[1].resize(HIST + BLOCK + 64);
         worker = std::thread([this]() {
             int w = 0;
+            uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+            uint64_t member_bytes = 0;
             for (;;) {
                 {
                     std::unique_lock<std::mutex> lk(mu);
                     cv.wait(lk, [&] { return ready[w] == 0 || abort_; });
                     if (abort_) return;
                 }
-                const int n = gzread(gz, blocks[w].data(), (unsigned)BLOCK);
-                const bool last = n <= 0;
+                long long n;
+                if (native) {
+                    // the last 32 KiB of the previous block are the window of the next one
+                    if (delivered) memcpy(blocks[w].data(), text(w ^ 1) + BLOCK - HIST, HIST);
+                    n = fill_native(w, crc, member_bytes);
+                    if (n == -1) {
+                        // The native decoder gave up (a stream it does not understand): hand the file to zlib, skip
+                        // what the parser already has, and carry on from there.  Corrupt data fails in zlib as well.
+                        native = false;
+                        std::string why = inflater.error();
+                        gz = gzopen(path_.c_str(), "rb");
+                        n = -3;
+                        if (gz) {
+                            gzbuffer(gz, 1 << 20);
+                            uint64_t skip = delivered;
+                            bool ok = true;
+                            while (skip && ok) {
+                                const unsigned chunk = (unsigned)std::min<uint64_t>(skip, BLOCK);
+                                ok = gzread(gz, text(w), chunk) == (int)chunk;
+                                skip -= chunk;
+                            }
+                            if (ok) n = gzread(gz, text(w), (unsigned)BLOCK);
+                        }
+                        if (n < 0) error_ = path_ + ": cannot inflate (" + why + ")";
+                    }
+                } else {
+                    n = gzread(gz, text(w), (unsigned)BLOCK);
+                }
+                if (!native && gz != nullptr && n < (long long)BLOCK && error_.empty()) {
+                    // end of file or failure: zlib reports a stream cut short (Z_BUF_ERROR) or corrupt data only here
+                    int errnum = Z_OK;
+                    const char* msg = gzerror(gz, &errnum);
+                    if (n < 0 || (errnum != Z_OK && errnum != Z_STREAM_END))
+                        error_ = path_ + ": " + (msg && *msg ? msg : "gzip stream is damaged or cut short");
+                }
+                const bool last = n <= 0 || (native && (size_t)n < BLOCK);
                 {
                     std::lock_guard<std::mutex> lk(mu);
                     lens[w] = n > 0 ? (size_t)n : 0;
                     ready[w] = 1;
                 }
                 cv.notify_all();
-                if (last) return;
+                if (n > 0) delivered += (uint64_t)n;
+                if (last && n <= 0) return;
+                if (last) {
+                    // a short native block is the end of the stream: publish the empty block that marks it
+                    w ^= 1;
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return ready[w] == 0 || abort_; });
+                    if (abort_) return;
+                    lens[w] = 0;
+                    ready[w] = 1;
+                    lk.unlock();
+                    cv.notify_all();
+                    return;
+                }
                 w ^= 1;
             }
         });
         wait_filled(0);
         return true;
+    }
+    // empty unless inflating failed; valid once next_line() has returned false
+    const std::string& error() {
+        std::lock_guard<std::mutex> lk(mu);
+        return error_;
     }
     void wait_filled(int b) {
         std::unique_lock<std::mutex> lk(mu);
@@ -204,11 +320,19 @@ struct LineSource {
         pos = 0;
         return lens[cur] != 0;
     }
+    // the unread rest of the current block, then the following blocks (raw byte stream; do not mix with next_line)
+    bool next_raw(const char*& b, size_t& n) {
+        if (pos >= lens[cur] && !next_block()) return false;
+        b = text(cur) + pos;
+        n = lens[cur] - pos;
+        pos = lens[cur];
+        return n != 0;
+    }
     // next line [begin, end) without the newline; returns false at end of file.  has_nl tells whether the line was
     // terminated (the reference counts newline characters, helpers.py:92-97).
     bool next_line(const char*& begin, const char*& end, bool& has_nl) {
         for (;;) {
-            const char* base = blocks[cur].data();
+            const char* base = text(cur);
             const size_t len = lens[cur];
             if (pos < len) {
                 const char* nl = static_cast<const char*>(memchr(base + pos, '\n', len - pos));
@@ -330,6 +454,24 @@ static int emit_names(const std::vector<std::string>& names, char* chrom_names, 
     return 0;
 }
 
+// The reader's decompressed byte stream of a file (what the parsers see): a diagnostic / test entry for the native
+// DEFLATE decoder.  Copies at most cap bytes into out (may be NULL) and returns the stream's total length in *n_out.
+extern "C" int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int64_t* n_out) {
+    EPI_REQUIRE(path != nullptr && n_out != nullptr, "null pointer argument");
+    LineSource src;
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    int64_t total = 0;
+    const char* b;
+    size_t n;
+    while (src.next_raw(b, n)) {
+        if (out != nullptr && total < cap) memcpy(out + total, b, (size_t)std::min<int64_t>((int64_t)n, cap - total));
+        total += (int64_t)n;
+    }
+    EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
+    *n_out = total;
+    return 0;
+}
+
 extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states,
                             int8_t* out, int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id,
                             char* chrom_names, int32_t chrom_names_cap, int32_t* n_chrom_out) {
@@ -342,13 +484,16 @@ extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, in
     const char *p, *e;
     bool has_nl;
     int64_t row = 0;
-    for (; row < row_lo; ++row)
-        EPI_REQUIRE(src.next_line(p, e, has_nl), "%s has only %lld rows, wanted rows from %lld", path, (long long)row,
-                    (long long)row_lo);
+    for (; row < row_lo; ++row) {
+        const bool got = src.next_line(p, e, has_nl);
+        EPI_REQUIRE(got || src.error().empty(), "%s", src.error().c_str());
+        EPI_REQUIRE(got, "%s has only %lld rows, wanted rows from %lld", path, (long long)row, (long long)row_lo);
+    }
     int last_id = -1;
     for (; row < row_hi; ++row) {
-        EPI_REQUIRE(src.next_line(p, e, has_nl), "%s ends after %lld rows, wanted rows up to %lld", path, (long long)row,
-                    (long long)row_hi);
+        const bool got = src.next_line(p, e, has_nl);
+        EPI_REQUIRE(got || src.error().empty(), "%s", src.error().c_str());
+        EPI_REQUIRE(got, "%s ends after %lld rows, wanted rows up to %lld", path, (long long)row, (long long)row_hi);
         const int64_t r = row - row_lo;
         int8_t* dst = out + r * pitch;
         int32_t cid = 0;
@@ -405,6 +550,7 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
         pf->chrom.push_back(cid);
         ++pf->rows;
     }
+    EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     size_t nb = 0;
     for (const std::string& s : pf->names) nb += s.size() + 1;
     if (rows_out) *rows_out = pf->rows;
@@ -563,6 +709,7 @@ extern "C" int epi_scores_tsv_open(const char* path, void** handle_out, int64_t*
         EPI_REQUIRE(p == e + 1, "%s: row %lld has more than %d score columns", path, (long long)r, sf->cols);
         ++sf->rows;
     }
+    EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     size_t nb = 0;
     for (const std::string& s : sf->names) nb += s.size() + 1;
     if (rows_out) *rows_out = sf->rows;

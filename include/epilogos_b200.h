@@ -171,6 +171,10 @@ int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pi
  *                     gzipped matrix is what bounds reading it): _open parses the whole file into a library-owned
  *                     staging area and reports rows / columns / chromosome names; _fetch copies a row range into the
  *                     caller's (pinned) buffers exactly as epi_pack_tsv would have written them; _close frees it. */
+/* Diagnostic: the decompressed byte stream the parsers see for `path` (gzip through the library's own DEFLATE decoder,
+ * csrc/fast_inflate.h, with CRC-32 / ISIZE checks per member; zlib with EPI_ZLIB_INFLATE=1; plain files as they are).
+ * Copies at most cap bytes to out (NULL allowed); *n_out = total length. */
+int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int64_t* n_out);
 int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
 int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out, int32_t* cols_out,
                        int32_t* n_chrom_out, int32_t* names_bytes_out);

@@ -117,3 +117,95 @@ def test_packer_long_lines_across_buffer_blocks(tmp_path):
     loc, s0 = helpers.read_matrix(f, num_states=25)
     assert np.array_equal(s0, x)
     assert loc["chrom"][0] == "chr1" and loc["chrom"][-1] == "chr2" and loc["start"][-1] == 39999 * 200
+
+
+# ---- the reader's own DEFLATE / gzip decoder (csrc/fast_inflate.h) against zlib ------------------------------------
+def _inflate(path, monkeypatch=None, use_zlib=False):
+    import ctypes
+    from epilogos_b200 import _lib
+    if monkeypatch is not None:
+        if use_zlib:
+            monkeypatch.setenv("EPI_ZLIB_INFLATE", "1")
+        else:
+            monkeypatch.delenv("EPI_ZLIB_INFLATE", raising=False)
+    n = ctypes.c_int64(0)
+    _lib.call("epi_inflate_file", str(path).encode(), ctypes.c_void_p(0), 0, ctypes.byref(n))
+    buf = np.empty(max(n.value, 1), dtype=np.uint8)
+    _lib.call("epi_inflate_file", str(path).encode(), ctypes.c_void_p(buf.ctypes.data), n.value, ctypes.byref(n))
+    return buf[:n.value].tobytes()
+
+
+def test_native_inflate_equals_zlib_on_every_block_type(tmp_path, monkeypatch):
+    """Stored, fixed-Huffman and dynamic-Huffman blocks, long codes (random bytes at level 9), short-period matches,
+    literal-only streams, sync / full flushes (empty stored blocks), multi-member files (what the score writer emits),
+    empty input, and a 40 MB stream that crosses the reader's 16 MB blocks in the middle of matches."""
+    import zlib
+    rng = np.random.default_rng(0)
+    alphabet = np.frombuffer(b"0123456789\t\n", dtype=np.uint8)
+    row = b"chr1\t0\t200\t" + b"\t".join(str(int(v)).encode() for v in rng.integers(1, 19, 833)) + b"\n"
+    cases = {
+        "empty": b"", "one": b"x", "text": b"chr1\t0\t200\t1\t2\t3\n" * 1000,
+        "random": rng.integers(0, 256, 300000, dtype=np.uint8).tobytes(),
+        "lowentropy": rng.choice(alphabet, 2_000_000, p=[.3, .2, .1, .05, .05, .05, .05, .04, .03, .03, .08, .02]).tobytes(),
+        "runs": b"a" * 70000 + b"ab" * 40000 + b"abc" * 30000 + b"abcdefg" * 20000 + bytes(range(256)) * 3000,
+        "blocks40MB": (row * 7 + rng.integers(48, 58, 1000, dtype=np.uint8).tobytes()) * 2000,
+    }
+    for name, data in cases.items():
+        variants = {}
+        for lvl in (0, 1, 6, 9) if len(data) < 10_000_000 else (1,):
+            variants["l%d" % lvl] = gzip.compress(data, lvl)
+        if len(data) < 10_000_000:
+            for tag, strategy in (("fixed", zlib.Z_FIXED), ("huffman", zlib.Z_HUFFMAN_ONLY), ("rle", zlib.Z_RLE)):
+                co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, strategy)
+                variants[tag] = co.compress(data) + co.flush()
+            step = max(len(data) // 7, 1)
+            variants["multi"] = b"".join(gzip.compress(data[i:i + step], 1 + (i % 9)) for i in range(0, max(len(data), 1), step))
+            co = zlib.compressobj(6, zlib.DEFLATED, 31)
+            out = b""
+            for j, i in enumerate(range(0, len(data), 50021)):
+                out += co.compress(data[i:i + 50021]) + co.flush(zlib.Z_SYNC_FLUSH if j % 2 else zlib.Z_FULL_FLUSH)
+            variants["flush"] = out + co.flush()
+            variants["padded"] = gzip.compress(data, 6) + b"\0" * 37            # zero padding after the last member
+        for tag, packed in variants.items():
+            p = tmp_path / ("%s_%s.gz" % (name, tag))
+            p.write_bytes(packed)
+            assert _inflate(p, monkeypatch) == data, (name, tag)
+    p = tmp_path / "plain.txt"
+    p.write_bytes(cases["text"])
+    assert _inflate(p, monkeypatch) == cases["text"]                            # not gzip: passed through
+    p = tmp_path / "text_l6.gz"
+    assert _inflate(p, monkeypatch, use_zlib=True) == cases["text"]             # EPI_ZLIB_INFLATE=1: the zlib path
+
+
+def test_damaged_gzip_is_an_error_not_a_short_read(tmp_path, monkeypatch):
+    """A stream that is cut short, fails its CRC-32 or holds invalid codes raises (the pandas reader of the reference
+    raises too); it is never returned as a shorter matrix.  Both decoders."""
+    rng = np.random.default_rng(1)
+    text = b"".join(b"chr1\t%d\t%d\t" % (i * 200, i * 200 + 200) + b"\t".join(str(int(v)).encode() for v in rng.integers(1, 19, 40)) + b"\n"
+                    for i in range(5000))
+    good = gzip.compress(text, 6)
+    p = tmp_path / "m.txt.gz"
+    damaged = {"cut in the data": good[:len(good) // 2], "cut in the trailer": good[:-3],
+               "crc": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:], "length": good[:-1] + bytes([good[-1] ^ 0x40]),
+               "data": good[:len(good) // 3] + bytes([good[len(good) // 3] ^ 0x10]) + good[len(good) // 3 + 1:]}
+    for use_zlib in (False, True):
+        for what, blob in damaged.items():
+            p.write_bytes(blob)
+            with pytest.raises(EpilogosB200Error):
+                _inflate(p, monkeypatch, use_zlib)
+            with pytest.raises(EpilogosB200Error):
+                helpers.read_matrix(p, num_states=18)
+        p.write_bytes(good)
+        loc, states = helpers.read_matrix(p, num_states=18)
+        assert states.shape == (5000, 40) and _inflate(p, monkeypatch, use_zlib) == text
+    # seeded single-bit damage anywhere in the file: rejected, or (header fields that carry no data) decoded in full
+    for trial in range(300):
+        blob = bytearray(good)
+        i = int(rng.integers(2, len(blob)))
+        blob[i] ^= 1 << int(rng.integers(0, 8))
+        p.write_bytes(bytes(blob))
+        try:
+            got = _inflate(p, monkeypatch)
+        except EpilogosB200Error:
+            continue
+        assert got == text, "byte %d flipped: accepted with different content" % i
