@@ -27,7 +27,7 @@ def _stale():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "epilogos_b200.h",
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "epilogos_b200.h",
                                                                   Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 

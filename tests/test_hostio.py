@@ -209,3 +209,27 @@ def test_damaged_gzip_is_an_error_not_a_short_read(tmp_path, monkeypatch):
         except EpilogosB200Error:
             continue
         assert got == text, "byte %d flipped: accepted with different content" % i
+
+
+def test_parser_fast_and_careful_paths_agree(tmp_path):
+    """One-, two- and three-digit labels mixed in every column position (the fast path takes the first two shapes, the
+    careful loop the rest and the last column), single-column files, and errors raised from inside long rows."""
+    rng = np.random.default_rng(5)
+    for cols, k in ((1, 5), (2, 9), (3, 127), (40, 127), (833, 18), (200, 100)):
+        x = rng.integers(1, k + 1, (300, cols))
+        p = tmp_path / ("m_%d_%d.txt" % (cols, k))
+        p.write_text("".join("chrZ\t%d\t%d\t%s\n" % (i * 200, i * 200 + 200, "\t".join(map(str, r))) for i, r in enumerate(x.tolist())))
+        loc, got = helpers.read_matrix(p, num_states=k)
+        assert np.array_equal(got, x - 1) and list(loc["start"][:2]) == [0, 200][:len(x)]
+    x = rng.integers(1, 19, (50, 600))
+    rows = ["chr1\t%d\t%d\t%s" % (i * 200, i * 200 + 200, "\t".join(map(str, r))) for i, r in enumerate(x.tolist())]
+    for bad_field, msg in (("19", "outside 1..18"), ("0", "outside 1..18"), ("1x", "unexpected character"), ("", "not an integer"),
+                           ("-3", "not an integer")):
+        broken = list(rows)
+        f = broken[17].split("\t")
+        f[3 + 411] = bad_field
+        broken[17] = "\t".join(f)
+        p = tmp_path / "bad.txt"
+        p.write_text("\n".join(broken) + "\n")
+        with pytest.raises(EpilogosB200Error, match="row 17.*" + msg):
+            helpers.read_matrix(p, num_states=18)
