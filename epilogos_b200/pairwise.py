@@ -17,7 +17,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import dist, session, writer
+from . import dist, helpers, session, writer
 from .scores import _gather_locations
 
 
@@ -72,7 +72,7 @@ def calculateScoresPairwise(saliency, file1Path, file2Path, numStates, outputDir
         writer.write_scores_text(outputDirPath / "pairwiseDelta_{}_{}.txt.gz".format(fileTag, filename),
                                  delta.cpu().numpy(), loc)
         chrName = loc["chrom"][0] if len(loc["chrom"]) else ""
-        np.savez_compressed(outputDirPath / "temp_nullDistances_{}_{}.npz".format(fileTag, filename),
+        helpers.savez_level(outputDirPath / "temp_nullDistances_{}_{}.npz".format(fileTag, filename),
                             chrName=np.array([chrName]), nullDistances=null_dist.cpu().numpy())
-        np.savez_compressed(outputDirPath / "temp_quiescence_{}_{}.npz".format(fileTag, filename),
+        helpers.savez_level(outputDirPath / "temp_quiescence_{}_{}.npz".format(fileTag, filename),
                             chrName=np.array([chrName]), quiescenceArr=quies.cpu().numpy().astype(np.bool_))

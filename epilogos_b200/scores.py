@@ -53,7 +53,7 @@ def calculateScores(saliency, file1Path, numStates, outputDirPath, expFreqPath, 
         scoreArr = scoreArr.cpu().numpy()
         writer.write_scores_text(outputDirPath / "scores_{}_{}.txt.gz".format(fileTag, filename), scoreArr, loc)
         chrName = loc["chrom"][0] if len(loc["chrom"]) else ""
-        np.savez_compressed(outputDirPath / "temp_scores_{}_{}.npz".format(fileTag, filename),
+        helpers.savez_level(outputDirPath / "temp_scores_{}_{}.npz".format(fileTag, filename),
                             chrName=np.array([chrName]), scoreArr=scoreArr, locationArr=writer.location_array(loc))
 
 

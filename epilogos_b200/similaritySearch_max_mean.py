@@ -41,20 +41,6 @@ def readScores(scoresPath):
     return loc, scores, rowSums(scores)
 
 
-def savez_level(path, level=1, **arrays):
-    """np.savez_compressed with a chosen deflate level: the same .npz container (np.load reads it), but level 1 instead of
-    zlib's default 6 -- these score matrices are dominated by repeated quiescent rows and pack almost as well at a
-    quarter of the time (whole chr1: 0.9 s instead of 3.2 s of a 5 s stage)."""
-    import zipfile
-    path = Path(path)
-    if path.suffix != ".npz":
-        path = path.with_name(path.name + ".npz")
-    with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=level) as zf:
-        for name, arr in arrays.items():
-            with zf.open(name + ".npy", "w", force_zip64=True) as f:
-                np.lib.format.write_array(f, np.asanyarray(arr), allow_pickle=True)
-
-
 def _coords(chrom, start, end):
     out = np.empty((len(chrom), 3), dtype=object)
     out[:, 0] = chrom
@@ -127,7 +113,7 @@ def main(outputDir, scoresPath, windowBins, blockSize, windowBP, filterState, fi
     outputDir = Path(outputDir)
     print("Reading in data...", flush=True); t = time()
     loc, stateScores, sums = readScores(scoresPath)
-    savez_level(outputDir / "genome_stats", scores=stateScores, coords=_coords(loc["chrom"], loc["start"], loc["end"]))
+    helpers.savez_level(outputDir / "genome_stats", scores=stateScores, coords=_coords(loc["chrom"], loc["start"], loc["end"]))
     # as many regions as could tile the genome (similaritySearch_max_mean.py:15-17)
     maxRegions = int(stateScores.shape[0] // windowBins)
     print("    Time:", format(time() - t, '.0f'), "seconds\n", flush=True)
@@ -144,7 +130,7 @@ def main(outputDir, scoresPath, windowBins, blockSize, windowBP, filterState, fi
 
     print("Filtering out uninteresting regions...", flush=True); t1 = time()
     roiCoords, roiCube = removeRegions(roiCoords, roiCube, filterState, filterScore)
-    savez_level(outputDir / "simsearch_cube", scores=roiCube, coords=roiCoords)
+    helpers.savez_level(outputDir / "simsearch_cube", scores=roiCube, coords=roiCoords)
     print("    Time:", format(time() - t1, '.0f'), "seconds\n", flush=True)
 
     print("Reducing genome scores by factor of {}...".format(blockSize), flush=True); t1 = time()
