@@ -233,3 +233,23 @@ def test_parser_fast_and_careful_paths_agree(tmp_path):
         p.write_text("\n".join(broken) + "\n")
         with pytest.raises(EpilogosB200Error, match="row 17.*" + msg):
             helpers.read_matrix(p, num_states=18)
+
+
+def test_native_inflate_reads_the_writers_multi_member_files_across_blocks(tmp_path, monkeypatch):
+    """What the score writer emits (one gzip member per 16384 rows) read back by the native decoder: dozens of member
+    boundaries, some of them inside a 16 MB reader block, CRC-32 / length checked for each; and the score reader on top."""
+    rng = np.random.default_rng(9)
+    rows, k = 600_000, 6
+    sc = (rng.gamma(0.5, 1.0, (rows, k)) * (rng.random((rows, 1)) < 0.4)).astype(np.float32)
+    loc = dict(chrom=np.array(["chr1"] * rows, dtype=object), start=np.arange(rows, dtype=np.int64) * 200,
+               end=np.arange(rows, dtype=np.int64) * 200 + 200)
+    p = tmp_path / "scores_big.txt.gz"
+    writer.write_scores_text(p, sc, loc)
+    with gzip.open(p, "rb") as f:
+        text = f.read()
+    assert len(text) > 2 * (16 << 20)
+    assert _inflate(p, monkeypatch) == text
+    assert _inflate(p, monkeypatch, use_zlib=True) == text
+    monkeypatch.delenv("EPI_ZLIB_INFLATE", raising=False)
+    _, got = helpers.read_scores(p)
+    assert got.shape == (rows, k) and np.array_equal(got[::997], np.array([[float("%.5f" % float(v)) for v in r] for r in sc[::997]]))
