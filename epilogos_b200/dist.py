@@ -6,8 +6,37 @@ import torch
 import torch.distributed as dist
 
 
+_solo = False
+
+
 def initialised():
-    return dist.is_available() and dist.is_initialized()
+    return (not _solo) and dist.is_available() and dist.is_initialized()
+
+
+class solo:
+    """Inside this context the calling rank behaves as a single-rank job (rank 0 of 1: no all-reduce, no gather, no
+    barrier), although a process group exists.  Used when whole input FILES, not row ranges, are dealt to the ranks: every
+    rank then runs the unsharded stage code on its own files and the ranks only meet at the barriers between stages."""
+
+    def __enter__(self):
+        global _solo
+        self.prev = _solo
+        _solo = True
+        return self
+
+    def __exit__(self, *exc):
+        global _solo
+        _solo = self.prev
+        return False
+
+
+def group_rank():
+    """Rank in the process group, also inside solo()."""
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def group_world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 def world_size():

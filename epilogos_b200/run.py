@@ -97,6 +97,70 @@ def checkArguments(mode, saliency, inputDirPath, inputDirPath2, outputDirPath, n
             return
 
 
+def deal_files(pairs, world):
+    """Whole files dealt to the ranks, largest first to the least loaded rank (by size on disk): the same answer on every
+    rank.  Returns a list of `world` lists of (file1, file2) pairs."""
+    sizes = [Path(f).stat().st_size + (Path(f2).stat().st_size if str(f2) != "null" else 0) for f, f2 in pairs]
+    order = sorted(range(len(pairs)), key=lambda i: (-sizes[i], str(pairs[i][0])))
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        out[r].append(pairs[i])
+        load[r] += sizes[i]
+    return [sorted(part, key=lambda pr: str(pr[0])) for part in out]
+
+
+def run_stages(pairs, mode, numStates, saliency, outputDirPath, fileTag, storedExpPath, numProcesses, quiescentState,
+               groupSize, stateInfo, roiWidth, verbose, say, backend=None):
+    """Steps 1-4 of run.main (run.py:193-303) in process.  Two ways to use several GPUs:
+      rows  (default)  every file's rows are split over the ranks (helpers.splitRows); per-file tables are all-reduced and
+                       score rows gathered on rank 0, which writes the files;
+      files (EPILOGOS_B200_SHARD=files, needs at least as many files as ranks)  whole files are dealt to the ranks, which
+                       run the unsharded stages on them and write their own outputs; the ranks meet at the barriers between
+                       the stages and the per-file count tables are combined from the files, as the reference's SLURM jobs
+                       do.  No file is inflated or parsed by more than one rank, and the text is written in parallel.
+    Integer tables make both identical to a single-rank run."""
+    from contextlib import nullcontext
+    from . import dist, expected, expectedCombination, scores, session
+    world = dist.world_size()
+    by_file = os.environ.get("EPILOGOS_B200_SHARD", "rows") == "files" and world > 1 and len(pairs) >= world
+    mine = deal_files(pairs, world)[dist.rank()] if by_file else pairs
+    alone = dist.solo if by_file else nullcontext
+    if by_file:
+        say("        Input files dealt to the ranks: {} files over {} GPUs".format(len(pairs), world))
+
+    with alone():
+        session.prefetch(mine, numStates, backend)       # parse all files concurrently, once (the stages re-use them)
+    say("\nSTEP 1: Per data file background frequency calculation")
+    with alone():
+        for f, f2 in mine:
+            expected.main(f, f2, numStates, saliency, outputDirPath, fileTag, numProcesses, verbose, backend=backend)
+    dist.barrier()
+    say("\nSTEP 2: Background frequency combination")
+    expectedCombination.main(outputDirPath, storedExpPath, fileTag, verbose, backend=backend)
+    say("\nSTEP 3: Score calculation")
+    with alone():
+        for f, f2 in mine:
+            scores.main(f, f2, numStates, saliency, outputDirPath, storedExpPath, fileTag, numProcesses, quiescentState,
+                        groupSize, verbose, backend=backend)
+    dist.barrier()
+    if mode == "single":
+        say("\nSTEP 4: Finding regions of interest")
+        try:
+            from . import roi
+        except ImportError:
+            roi = None
+        if roi is None:
+            say("    (region-of-interest selection is not part of this build; temp_scores_*.npz kept for roiSingle)")
+        elif dist.rank() == 0:
+            roi.main(outputDirPath, stateInfo, fileTag, storedExpPath, roiWidth, verbose)
+    else:
+        say("\nSTEP 4: p-values, regions of interest and figures are produced by the reference's "
+            "roiAndVisualPairwise from pairwiseDelta_*, temp_nullDistances_* and temp_quiescence_* in "
+            + str(outputDirPath))
+
+
 @click.command(context_settings=dict(help_option_names=["-h", "--help"]))
 @click.option("-m", "--mode", "mode", type=click.Choice(["single", "paired"]), default="single", show_default=True,
               help="single for single group epilogos and paired for 2 group epilogos")
@@ -201,31 +265,8 @@ def main(mode, commandLineBool, inputDirectory, inputDirectory1, inputDirectory2
                                         + "directories 1 and 2 have the same name")
             pairs.append((f, match))
 
-    from . import session
-    session.prefetch(pairs, numStates)                   # parse all files concurrently, once (the stages re-use them)
-    say("\nSTEP 1: Per data file background frequency calculation")
-    for f, f2 in pairs:
-        expected.main(f, f2, numStates, saliency, outputDirPath, fileTag, numProcesses, verbose)
-    say("\nSTEP 2: Background frequency combination")
-    expectedCombination.main(outputDirPath, storedExpPath, fileTag, verbose)
-    say("\nSTEP 3: Score calculation")
-    for f, f2 in pairs:
-        scores.main(f, f2, numStates, saliency, outputDirPath, storedExpPath, fileTag, numProcesses, quiescentState,
-                    groupSize, verbose)
-    if mode == "single":
-        say("\nSTEP 4: Finding regions of interest")
-        try:
-            from . import roi
-        except ImportError:
-            roi = None
-        if roi is None:
-            say("    (region-of-interest selection is not part of this build; temp_scores_*.npz kept for roiSingle)")
-        elif lead:
-            roi.main(outputDirPath, stateInfo, fileTag, storedExpPath, roiWidth, verbose)
-    else:
-        say("\nSTEP 4: p-values, regions of interest and figures are produced by the reference's "
-            "roiAndVisualPairwise from pairwiseDelta_*, temp_nullDistances_* and temp_quiescence_* in "
-            + str(outputDirPath))
+    run_stages(pairs, mode, numStates, saliency, outputDirPath, fileTag, storedExpPath, numProcesses, quiescentState,
+               groupSize, stateInfo, roiWidth, verbose, say)
     dist.barrier()
     if launched and td.is_initialized():
         td.destroy_process_group()

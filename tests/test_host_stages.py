@@ -227,3 +227,74 @@ def test_paired_pipeline_files_match_reference(tmp_path, golden, name):
         assert null.dtype == np.float32 and null.tobytes() == g["s%d_null" % s].tobytes()
         assert quies.dtype == np.bool_ and np.array_equal(quies, g["s%d_quiescence" % s])
         assert text == g["s%d_delta_text" % s].tobytes()
+
+
+FILES_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+os.environ["EPILOGOS_B200_SHARD"] = {shard!r}
+import torch.distributed as td
+from pathlib import Path
+from fake_backend import OracleBackend
+from epilogos_b200 import dist, run
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+out = Path({out!r}); inp = Path({inp!r})
+pairs = [(f, "null") for f in sorted(inp.glob("*"))]
+lead = dist.rank() == 0
+say = (lambda *a, **k: print(*a, **k, flush=True)) if lead else (lambda *a, **k: None)
+run.run_stages(pairs, "single", 18, 2, out, "in_s2", out / "exp_freq_in_s2.npy", 1, 17, -1, {meta!r}, 20, False, say,
+               backend=OracleBackend())
+print("RANK", td.get_rank(), "files", sorted(p.name for p in out.glob("scores_*")), flush=True)
+td.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("shard", ["files", "rows"])
+def test_run_stages_world_size_two_files_or_rows(tmp_path, golden, shard):
+    """run.run_stages on two gloo ranks with three input files of different sizes: whole files dealt to the ranks
+    (EPILOGOS_B200_SHARD=files: each rank runs the unsharded stages on its files, tables meet through the files) and rows
+    split over the ranks (default) both reproduce the single-rank result -- table, every score file, ROI list."""
+    from oracle import epilogos_oracle as orc
+    from test_cli import META
+    g = golden("real10_chr1_k18")
+    x = g["x"]
+    parts = {"epilogos_matrix_chr1": x[:1700], "epilogos_matrix_chr2": x[1700:2300], "epilogos_matrix_chrX": x[2300:3301]}
+    inp = tmp_path / "in"; out = tmp_path / "out"
+    inp.mkdir(); out.mkdir()
+    for name, part in parts.items():
+        write_tsv(inp / (name + ".txt"), part, chrom=name.split("_")[-1])
+    meta = tmp_path / "meta.tsv"
+    meta.write_text(META)
+    port = 31500 + (os.getpid() % 2000) + (7 if shard == "files" else 0)
+    code = FILES_WORKER.format(root=str(ROOT), tests=str(ROOT / "tests"), port=port, out=str(out), inp=str(inp),
+                               meta=str(meta), shard=shard)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    logs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    if shard == "files":
+        assert "Input files dealt to the ranks: 3 files over 2 GPUs" in logs[0]
+    allx = np.concatenate(list(parts.values()))
+    exp = orc.normalize_expected(orc.s2_expected_counts(allx, 18))
+    for name, part in parts.items():
+        ref = orc.s2_scores(part, 18, exp)
+        with gzip.open(out / ("scores_in_s2_%s.txt.gz" % name), "rb") as gzf:
+            text = gzf.read()
+        starts = np.arange(part.shape[0]) * 200
+        assert text == orc.format_scores_text(ref, name.split("_")[-1], starts, starts + 200)
+    # step 4 ran once, on rank 0, over every file's scores, and cleaned up
+    assert (out / "regionsOfInterest_in_s2.txt").exists() and not list(out.glob("temp_*")) and not (out / "exp_freq_in_s2.npy").exists()
+    assert len((out / "regionsOfInterest_in_s2.txt").read_text().splitlines()) > 10
+
+
+def test_deal_files_balances_by_size(tmp_path):
+    from epilogos_b200 import run
+    sizes = {"a": 900, "b": 500, "c": 400, "d": 300, "e": 100}
+    pairs = []
+    for n, s in sizes.items():
+        (tmp_path / n).write_bytes(b"x" * s)
+        pairs.append((tmp_path / n, "null"))
+    dealt = run.deal_files(pairs, 2)
+    loads = [sum(sizes[p[0].name] for p in part) for part in dealt]
+    assert sorted(p[0].name for part in dealt for p in part) == sorted(sizes) and abs(loads[0] - loads[1]) <= 200
+    assert run.deal_files(pairs, 2) == dealt                   # deterministic: every rank computes the same deal
