@@ -63,3 +63,33 @@ def test_local_single_pipeline_end_to_end(tmp_path, golden):
     want = roi_oracle.roi_text(np.array(["chr1"] * len(x), dtype=object), sel, states, ["S%d" % i for i in range(1, 19)])
     got = (out / "regionsOfInterest_mydata_s1.txt").read_text()
     assert [l.split("\t")[:4] for l in got.splitlines()] == [l.split("\t")[:4] for l in want.splitlines()]
+
+
+def test_cli_main_end_to_end_on_cpu_with_the_oracle_backend(tmp_path, golden, monkeypatch):
+    """The whole `epilogos -l` command path (argument checks, file discovery, prefetch, steps 1-4, clean-up) without a
+    GPU: the session's backend is replaced by the oracle-backed stand-in of the host-stage tests, so this covers
+    run.main / run.run_stages themselves; the GPU test above covers the same path with the CUDA backend."""
+    from fake_backend import OracleBackend
+    from epilogos_b200 import run, session
+    from oracle import epilogos_oracle as orc
+    session.clear()
+    monkeypatch.setattr(session, "_backend", OracleBackend())
+    x = golden("real10_chr1_k18")["x"][:1500]
+    inp = tmp_path / "mydata"; out = tmp_path / "out"
+    inp.mkdir()
+    write_tsv(inp / "epilogos_matrix_chr1.txt.gz", x[:900], gz=True)
+    write_tsv(inp / "epilogos_matrix_chr2.txt.gz", x[900:], chrom="chr2", gz=True)
+    meta = tmp_path / "meta.tsv"
+    meta.write_text(META)
+    r = CliRunner().invoke(run.main, ["-l", "-i", str(inp), "-o", str(out), "-j", str(meta), "-s", "2", "-w", "20"])
+    assert r.exit_code == 0, r.output + repr(r.exception)
+    assert "STEP 1" in r.output and "STEP 4" in r.output
+    exp = orc.normalize_expected(orc.s2_expected_counts(x, 18))
+    for name, part, chrom in (("chr1", x[:900], "chr1"), ("chr2", x[900:], "chr2")):
+        with gzip.open(out / ("scores_mydata_s2_epilogos_matrix_%s.txt.gz" % name), "rb") as f:
+            text = f.read()
+        starts = np.arange(len(part)) * 200
+        assert text == orc.format_scores_text(orc.s2_scores(part, 18, exp), chrom, starts, starts + 200)
+    assert (out / "regionsOfInterest_mydata_s2.txt").exists()
+    assert not list(out.glob("temp_*")) and not (out / "exp_freq_mydata_s2.npy").exists()
+    session.clear()
