@@ -51,6 +51,39 @@ def calculateExpected(saliency, shard, numStates, backend=None):
     return counts.cpu().numpy().astype(np.int64, copy=False)
 
 
+def _rows_matrix(file1Path, file2Path, rowsToCalc, numStates):
+    rows = (int(rowsToCalc[0]), int(rowsToCalc[1]))
+    _, x = helpers.read_matrix(file1Path, rows, want_locations=False, num_states=numStates)
+    if str(file2Path) != "null":
+        _, xb = helpers.read_matrix(file2Path, rows, want_locations=False, num_states=numStates)
+        x = np.concatenate((x, xb), axis=1)               # the union of both groups (helpers.py:173-179)
+    return x
+
+
+def s1Calc(file1Path, file2Path, rowsToCalc, numStates, verbose, backend=None):
+    """The reference's per-chunk worker under its own name (expected.py:90-116): int64 [numStates] label counts of rows
+    [rowsToCalc[0], rowsToCalc[1]) of the file (of both files side by side in paired mode), computed on the GPU."""
+    be = session.get_backend(backend)
+    x = _rows_matrix(file1Path, file2Path, rowsToCalc, numStates)
+    return be.expected_table(be.counts(x, numStates), x.shape[1], 1).cpu().numpy().astype(np.int64, copy=False)
+
+
+def s2Calc(file1Path, file2Path, rowsToCalc, numStates, verbose, backend=None):
+    """expected.py:119-162: int64 [numStates, numStates] ordered-pair counts of the rows."""
+    be = session.get_backend(backend)
+    x = _rows_matrix(file1Path, file2Path, rowsToCalc, numStates)
+    return be.expected_table(be.counts(x, numStates), x.shape[1], 2).cpu().numpy().astype(np.int64, copy=False)
+
+
+def s3Calc(file1Path, rowsToCalc, numStates, verbose, backend=None):
+    """expected.py:165-204: [C, C, numStates, numStates] counts of (biosample pair, state pair) over the rows (int32 in
+    the reference's worker, summed to int64 by its caller; int64 here)."""
+    be = session.get_backend(backend)
+    x = _rows_matrix(file1Path, "null", rowsToCalc, numStates)
+    tiles, plan = be.s3_tiles(be.states_to_device(x), x.shape[1], numStates)
+    return be.s3_counts(tiles, plan, x.shape[1], numStates, x.shape[0]).cpu().numpy().astype(np.int64, copy=False)
+
+
 def storeExpArray(expFreqArr, outputDirPath, fileTag, filename):
     expFreqPath = Path(outputDirPath) / "temp_exp_freq_{}_{}.npy".format(fileTag, filename)
     np.save(expFreqPath, expFreqArr, allow_pickle=False)

@@ -124,6 +124,35 @@ def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=Fal
     return loc, states0
 
 
+def readStates(file1Path=Path("null"), file2Path=Path("null"), rowsToCalc=(0, 0), expBool=True, verbose=True, groupSize=-1,
+               numStates=127):
+    """The reference's reader under its own name and return convention (helpers.py:123-194), for callers written
+    against it: 0-based `int` arrays of rows [rowsToCalc[0], rowsToCalc[1]).
+        single:                  file1Arr
+        paired, expBool=True:    [file1Arr | file2Arr]
+        paired, expBool=False:   file1Arr, file2Arr and the two halves of the per-row shuffle of [file1Arr | file2Arr]
+                                 (np.argsort(np.random.rand(rows, N), axis=1): the same draws from numpy's global generator
+                                 as the reference, so a seeded caller gets the reference's shuffle), cut at file1Arr's width
+                                 or into two groups of groupSize.
+    The stage drivers do not go through this shim (they keep the int8 matrix of read_matrix and shuffle on the device);
+    `numStates` only bounds the label check of the native parser."""
+    rows = (int(rowsToCalc[0]), int(rowsToCalc[1]))
+    _, a = read_matrix(file1Path, rows, want_locations=False, num_states=numStates)
+    file1Arr = a.astype(int)
+    if str(file2Path) == "null":
+        return file1Arr
+    _, b = read_matrix(file2Path, rows, want_locations=False, num_states=numStates)
+    file2Arr = b.astype(int)
+    combinedArr = np.concatenate((file1Arr, file2Arr), axis=1)
+    if expBool:
+        return combinedArr
+    randomIndices = np.argsort(np.random.rand(*combinedArr.shape), axis=1)
+    shuffled = np.take_along_axis(combinedArr, randomIndices, axis=1)
+    if groupSize == -1:
+        return file1Arr, file2Arr, shuffled[:, :file1Arr.shape[1]], shuffled[:, file1Arr.shape[1]:]
+    return file1Arr, file2Arr, shuffled[:, :groupSize], shuffled[:, groupSize:2 * groupSize]
+
+
 def read_scores(path):
     """Parse a score file `chr start end score_1 .. score_K` (scores_*.txt.gz) with the native reader:
     returns (locations dict as read_matrix, float64 [rows, K] scores).  Replaces the pandas read of

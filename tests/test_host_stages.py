@@ -298,3 +298,45 @@ def test_deal_files_balances_by_size(tmp_path):
     loads = [sum(sizes[p[0].name] for p in part) for part in dealt]
     assert sorted(p[0].name for part in dealt for p in part) == sorted(sizes) and abs(loads[0] - loads[1]) <= 200
     assert run.deal_files(pairs, 2) == dealt                   # deterministic: every rank computes the same deal
+
+
+def test_readStates_shim_matches_the_reference_conventions(tmp_path):
+    """helpers.readStates (the reference's name and return convention): row ranges, 0-based int arrays, the paired
+    concatenation, and the seeded shuffle equal to the oracle's restatement of helpers.py:183-194."""
+    from epilogos_b200 import helpers
+    from oracle import epilogos_oracle as orc
+    xa = orc.synth_states(40, 7, 18, seed=1)
+    xb = orc.synth_states(40, 5, 18, seed=2)
+    fa, fb = tmp_path / "a.txt", tmp_path / "b.txt.gz"
+    write_tsv(fa, xa)
+    write_tsv(fb, xb, gz=True)
+    got = helpers.readStates(fa, rowsToCalc=(3, 31), verbose=False)
+    assert got.dtype == np.dtype(int) and np.array_equal(got, xa[3:31])
+    both = helpers.readStates(fa, fb, (0, 40), expBool=True, verbose=False)
+    assert np.array_equal(both, np.concatenate((xa, xb), axis=1))
+    for group in (-1, 4):
+        np.random.seed(123)
+        a, b, sa, sb = helpers.readStates(fa, fb, (5, 25), expBool=False, verbose=False, groupSize=group)
+        perm = orc.reference_shuffle_indices(123, 20, 12)
+        wa, wb = orc.paired_split(xa[5:25], xb[5:25], perm, group)[-2:]
+        assert np.array_equal(a, xa[5:25]) and np.array_equal(b, xb[5:25])
+        assert np.array_equal(sa, wa) and np.array_equal(sb, wb)
+
+
+def test_expected_chunk_workers_under_the_reference_names(tmp_path):
+    """expected.s1Calc / s2Calc (the reference's per-chunk workers, expected.py:90-162) on a row range, single and paired."""
+    from epilogos_b200 import expected
+    from fake_backend import OracleBackend
+    from oracle import epilogos_oracle as orc
+    xa = orc.synth_states(60, 9, 18, seed=3)
+    xb = orc.synth_states(60, 6, 18, seed=4)
+    fa, fb = tmp_path / "a.txt", tmp_path / "b.txt"
+    write_tsv(fa, xa)
+    write_tsv(fb, xb)
+    be = OracleBackend()
+    n1 = expected.s1Calc(fa, "null", (10, 50), 18, False, backend=be)
+    n2 = expected.s2Calc(fa, "null", (10, 50), 18, False, backend=be)
+    assert n1.dtype == np.int64 and np.array_equal(n1, orc.s1_expected_counts_rowloop(xa[10:50], 18))
+    assert n2.dtype == np.int64 and np.array_equal(n2, orc.s2_expected_counts_rowloop(xa[10:50], 18))
+    both = np.concatenate((xa, xb), axis=1)
+    assert np.array_equal(expected.s2Calc(fa, fb, (0, 60), 18, False, backend=be), orc.s2_expected_counts(both, 18))
