@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-target", action="store_true", help="skip the strong-scaling target sections (S2 / S1 genome, S3 chr1)")
     return ap.parse_args()
 
 
@@ -62,8 +63,110 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's row-loop port of expected+scores, all host cores, bounded sample
+# CPU arm.  kind "reference": the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_reference.py from
+# /root/reference) runs its own expected.main -> expectedCombination.main -> scores.main on a TSV.gz sample of the
+# workload with one worker process per host core -- what `epilogos -l -c 0` executes before the ROI step (run.py:191-279),
+# TSV parse and gz write included; its own verbose timers give the compute-only share.  kind "port": the oracle's
+# row-loop port (same algorithm and cost, I/O excluded), the fallback when the reference was not staged.
 # ------------------------------------------------------------------------------------------------
+def config_dict(args, world, bins, cols, k, desc, pitch=None):
+    """The `config` object of the JSON line: identical for our arm and the reference arm."""
+    saliency = 1 if args.config.startswith("paired") else int(args.config[1])
+    return {"workload": desc, "bins_per_gpu": bins, "biosamples": cols, "states": k, "saliency": saliency,
+            "distribution": args.kind,
+            "parallelism": "bins sharded x%d, integer table allreduce" % world,
+            "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (bins * (pitch or ((cols + 15) & ~15)) / 1e9)}
+
+
+def _reference_staged():
+    try:
+        from oracle import stage_reference
+        return stage_reference.staged_root() is not None
+    except Exception:
+        return False
+
+
+def _sample_files(workdir, config, bins, cols, k, kind, seed=4242):
+    """Write the TSV.gz sample of `bins` rows of the configuration; returns (file1, file2)."""
+    from oracle import epilogos_oracle as orc
+    from oracle import reference_driver as ref
+    workdir = Path(workdir)
+    if config.startswith("paired"):
+        a, b = workdir / "A", workdir / "B"
+        a.mkdir(exist_ok=True)
+        b.mkdir(exist_ok=True)
+        ref.write_matrix_tsv_gz(a / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 400, k, seed, kind))
+        ref.write_matrix_tsv_gz(b / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 433, k, seed + 1, kind))
+        return a / "epilogos_matrix_chr1.txt.gz", b / "epilogos_matrix_chr1.txt.gz"
+    d = workdir / "in"
+    d.mkdir(exist_ok=True)
+    f = d / "epilogos_matrix_chr1.txt.gz"
+    ref.write_matrix_tsv_gz(f, orc.synth_states(bins, cols, k, seed, kind))
+    return f, "null"
+
+
+def _s3_workers(cores, cols, k):
+    """scores.s3Score needs ~6 x the float32 [C,C,K,K] table per worker (masked temporaries of klScoreND, scores.py:479-480)
+    and expected.s3Calc pickles one int32 table per worker back: cap the pool by the memory that is available."""
+    table = cols * cols * k * k * 4
+    avail = 64 << 30
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return max(1, min(cores, int(avail * 0.6 // (7 * table + (1 << 30)))))
+
+
+def reference_cpu_arm(args, steps, warmup, budget_s):
+    """Times the staged reference on bounded samples.  Returns (dict cpu_baseline, list of per-step seconds, bins per step)."""
+    import tempfile
+    from oracle import reference_driver as ref
+    bins_full, cols, k, _ = CONFIGS[args.config]
+    paired = args.config.startswith("paired")
+    saliency = 1 if paired else int(args.config[1])
+    cores = os.cpu_count() or 1
+    nproc = _s3_workers(cores, cols, k) if saliency == 3 else cores
+    per_step = max(2.0, min(20.0, budget_s / max(1, steps + warmup)))
+    unit = 2 if saliency == 3 else 64                  # rows per worker in the smallest probe
+    with tempfile.TemporaryDirectory(prefix="epi_ref_") as d:
+        # two-point calibration t(n) = a + b n on warm imports (a = pool start-up, table load / store, first-row parse)
+        n1, n2 = nproc * unit, nproc * unit * 4
+        probe = []
+        for n in (n1, n1, n2):                         # the first run also pays the imports: dropped
+            f1, f2 = _sample_files(d, args.config, n, cols, k, args.kind)
+            probe.append(ref.time_pipeline(f1, f2, k, saliency, nproc, d)[0])
+        t1, t2 = probe[1], probe[2]
+        b = max((t2 - t1) / (n2 - n1), 1e-7)
+        a = max(t1 - b * n1, 0.0)
+        n = int(max(n2, min(bins_full, 400_000, (per_step - a) / b)))
+        n = max(nproc, n // nproc * nproc)
+        f1, f2 = _sample_files(d, args.config, n, cols, k, args.kind)
+        times, compute = [], []
+        for it in range(warmup + steps):
+            wall, comp = ref.time_pipeline(f1, f2, k, saliency, nproc, d, verbose_timers=(it == warmup + steps - 1))
+            if it >= warmup:
+                times.append(wall)
+            if comp:
+                compute.append(comp)
+    sec = sum(times) / len(times)
+    what = "paired S1 (groups of 400 + 433 biosamples, one null shuffle per bin)" if paired else "S%d" % saliency
+    base = dict(value=n / sec, unit="bins/s", cores=nproc, kind="reference",
+                sample="%d bins x %d biosamples x %d states as TSV.gz, %s: the unmodified reference's expected.main -> "
+                       "expectedCombination.main -> scores.main with %d worker processes (what `epilogos -l` runs before the "
+                       "ROI step), TSV parse and scores gz write included; %.2f s per pass, fixed cost %.2f s"
+                       % (n, cols, k, what, nproc, sec, a),
+                host_cores=cores)
+    if compute:
+        # the last pass ran with the reference's verbose timers on: compute loops of the first worker (all workers get
+        # equal row ranges and run concurrently), I/O and process start-up excluded
+        base["compute_only"] = {"value": n / compute[-1], "unit": "bins/s",
+                                "how": "reference's own verbose timers (expected.py:114,160,202; scores.py:324,423,506), "
+                                       "first worker, last pass"}
+    return base, times, n
+
+
 def _cpu_worker(args):
     from oracle import epilogos_oracle as orc
     bins, cols, k, saliency, seed, phase, exp = args
@@ -98,19 +201,18 @@ def _gen_worker(args):
     return int(orc.synth_states(bins, cols, k, seed).sum())
 
 
-def cpu_baseline(cols, k, saliency, budget_s=12.0, steps=1, warmup=0):
+def port_cpu_arm(cols, k, saliency, steps, warmup, budget_s):
+    """Fallback when the reference is not staged: the oracle's row-loop port, S1 / S2 only."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
+    per_step = max(2.0, min(20.0, budget_s / max(1, steps + warmup)))
     with ctx.Pool(cores) as pool:
-        # calibrate on a small pass, then size the sample for ~budget_s
-        probe = 64
-        t = cpu_port_pass(pool, cores, probe, cols, k, saliency, 1000)
-        tg0 = time.perf_counter()
-        pool.map(_gen_worker, [(probe, cols, k, 1000 + i) for i in range(cores)])
-        tgen = 2 * (time.perf_counter() - tg0)
-        rate = probe / max(t - tgen, 1e-3)
-        per_core = int(max(64, min(20000, rate * budget_s)))
+        cpu_port_pass(pool, cores, 64, cols, k, saliency, 900)                 # warm pool and imports
+        t1 = cpu_port_pass(pool, cores, 256, cols, k, saliency, 1000)
+        t2 = cpu_port_pass(pool, cores, 1024, cols, k, saliency, 1100)
+        b = max((t2 - t1) / 768.0, 1e-7)
+        per_core = int(max(256, min(50000, (per_step - max(t1 - 256 * b, 0.0)) / b)))
         times = []
         for it in range(warmup + steps):
             tt = cpu_port_pass(pool, cores, per_core, cols, k, saliency, 2000 + 100 * it)
@@ -124,7 +226,16 @@ def cpu_baseline(cols, k, saliency, budget_s=12.0, steps=1, warmup=0):
     return dict(value=total / sec, unit="bins/s", cores=cores, kind="port",
                 sample="%d bins x %d biosamples x %d states (S%d expected+scores, %d worker processes x %d bins, "
                        "row-loop port of expected.py/scores.py, I/O excluded)" % (total, cols, k, saliency, cores,
-                                                                                  per_core)), sec
+                                                                                  per_core)), times, total
+
+
+def cpu_arm(args, steps, warmup, budget_s):
+    if _reference_staged():
+        return reference_cpu_arm(args, steps, warmup, budget_s)
+    _, cols, k, _ = CONFIGS[args.config]
+    if args.config.startswith("paired") or args.config[1] == "3":
+        raise RuntimeError("the reference is not staged under oracle/_ref and the port covers S1/S2 only")
+    return port_cpu_arm(cols, k, int(args.config[1]), steps, warmup, budget_s)
 
 
 def run_reference(args):
@@ -132,26 +243,24 @@ def run_reference(args):
     if rank != 0:
         return
     bins, cols, k, desc = CONFIGS[args.config]
-    if args.config.startswith("paired"):
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the headline S1/S2 configurations only"}),
-              flush=True)
-        return
-    saliency = int(args.config[1])
-    if saliency == 3:
-        print(json.dumps({"impl": "reference", "unavailable": "S3 row-loop port needs ~1 s per bin at 833 biosamples; "
-                          "see profiles/ for the sampled figure"}), flush=True)
-        return
-    base, sec = cpu_baseline(cols, k, saliency, budget_s=6.0, steps=max(1, args.steps), warmup=args.warmup)
+    paired = args.config.startswith("paired")
+    saliency = 1 if paired else int(args.config[1])
+    steps, warmup = max(1, args.steps), args.warmup
+    if saliency == 3:               # one pass costs tens of seconds of fixed set-up per worker (693k-tuple pair list, 0.9 GB tables)
+        steps, warmup = min(steps, 2), 0
+    base, times, n = cpu_arm(args, steps, warmup, budget_s=150.0)
+    sec = sum(times) / len(times)
+    metric = ("bins/sec for paired expected+scores (S1)" if paired else "bins/sec for expected+scores (S%d)" % saliency)
     line = {
-        "impl": "reference", "metric": "bins/sec for expected+scores (S%d)" % saliency, "value": base["value"],
-        "unit": "bins/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric, "value": base["value"],
+        "unit": "bins/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int64+f64", "data": "synthetic",
-        "config": {"workload": desc, "biosamples": cols, "states": k, "saliency": saliency,
-                   "note": "each step is a bounded sample of the workload on the host CPU"},
+        "dtype": "int64+f64" if saliency != 3 else "int32+f32 (the reference's S3 arithmetic)", "data": "synthetic",
+        "config": config_dict(args, max(1, args.gpus), bins, cols, k, desc),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "bins_per_step": n,
+        "note": "each step is one pass of the reference over a bounded sample of the workload on the host CPU",
     }
     print(json.dumps(line), flush=True)
 
@@ -228,6 +337,155 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _timed_loop(torch, dist, world, stream, fn, steps):
+    """barrier + synchronize, `steps` calls of fn() between two CUDA events on the launching stream, synchronize + barrier;
+    returns ms per step, MAX over the ranks."""
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(steps):
+        fn()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _make_step(torch, dist, engine, world, x, cols, k, saliency, cnt, scores):
+    """One pass of the S1/S2 hot path over the resident matrix x; returns (step function, dict with the last tables)."""
+    last = {}
+
+    def step():
+        engine.bin_counts(x, cols, k, out=cnt)                                                      # K1
+        n1, n2 = engine.expected_tables(cnt, cols, want_s1=saliency == 1, want_s2=saliency == 2)    # K2
+        n = n1 if saliency == 1 else n2
+        if world > 1 and not os.environ.get("EPI_BENCH_SKIP_ALLREDUCE"):
+            dist.all_reduce(n)                                                                      # the path's only exchange
+        e = engine.normalize(n)                                                                     # K4
+        if saliency == 1:
+            engine.scores_s1(cnt, cols, e, out32=scores)                                            # K5
+        else:
+            engine.scores_s2(cnt, cols, e, out32=scores)
+        last["n"], last["e"] = n, e
+    return step, last
+
+
+def _check_step(torch, dist, world, last, total_bins, cols, saliency, scores):
+    """Correctness carried by the benchmark line itself: the all-reduced integer table must sum to its closed form
+    (S1: bins C, S2: bins C (C-1)) on every rank, every rank must hold the same table, and the scores are finite."""
+    want = total_bins * cols * (cols - 1 if saliency == 2 else 1)
+    got = int(last["n"].sum().item())
+    ok = got == want and bool(torch.isfinite(scores[:: max(1, scores.shape[0] // 65536)]).all())
+    if world > 1:
+        ref = last["n"].clone()
+        dist.broadcast(ref, src=0)
+        ok = ok and bool(torch.equal(ref, last["n"]))
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    return "ok" if ok else "FAILED: table sum %d, closed form %d" % (got, want), want
+
+
+def _strong_section(torch, dist, engine, world, x, cols, k, saliency, total_bins, steps):
+    """The north-star target configuration: ONE whole genome (total_bins) sharded over the `world` GPUs (strong scaling).
+    Every rank runs the step on total_bins / world rows; timed eagerly and as a captured CUDA graph (at 1/8 of a genome the
+    step is ~0.4 ms and the ~8 launches + the all-reduce are a visible fixed cost)."""
+    stream = torch.cuda.current_stream()
+    lo, hi = total_bins * int(os.environ.get("RANK", "0")) // world, total_bins * (int(os.environ.get("RANK", "0")) + 1) // world
+    rows = hi - lo
+    xs = x[:rows]
+    cnt = torch.empty((rows, k), dtype=torch.int16, device="cuda")
+    scores = torch.empty((rows, k), dtype=torch.float32, device="cuda")
+    step, last = _make_step(torch, dist, engine, world, xs, cols, k, saliency, cnt, scores)
+    for _ in range(3):
+        step()
+    eager_ms = _timed_loop(torch, dist, world, stream, step, steps)
+    check, _ = _check_step(torch, dist, world, last, total_bins, cols, saliency, scores)
+    out = {"bins_total": total_bins, "bins_per_gpu": rows, "saliency": saliency, "ms_per_step_eager": eager_ms,
+           "value_eager": total_bins / (eager_ms * 1e-3), "check": check}
+    graph_ms = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            step()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                step()
+        stream.wait_stream(side)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            g.replay()
+        graph_ms = _timed_loop(torch, dist, world, stream, g.replay, steps)
+        check_g, _ = _check_step(torch, dist, world, last, total_bins, cols, saliency, scores)
+        out.update({"ms_per_step_graph": graph_ms, "value_graph": total_bins / (graph_ms * 1e-3), "check_graph": check_g})
+        del g
+    except Exception as exc:                       # capture is an optimisation: report why it was not available
+        out["graph_error"] = str(exc)[:200]
+        torch.cuda.synchronize()
+    best = min(eager_ms, graph_ms) if graph_ms else eager_ms
+    out.update({"ms_per_step": best, "value": total_bins / (best * 1e-3), "unit": "bins/s", "scaling": "strong"})
+    return out
+
+
+def _s3_strong_section(torch, dist, engine, synth, world, rank, total_bins, cols, k, steps=2):
+    """BASELINE configs[2] sharded over the GPUs: chr1 (1.25 M bins) split in `world` row ranges; every rank builds the
+    tiles of its rows' one-hot Gram matrix, the ranks all-reduce the 464 MB int32 tile buffer (timed separately), every
+    rank finalises the table and scores its own rows."""
+    stream = torch.cuda.current_stream()
+    lo, hi = total_bins * rank // world, total_bins * (rank + 1) // world
+    rows = hi - lo
+    x = synth.synth_states_device(rows, cols, k, seed=4321 + rank)
+    plan = engine.s3_plan(rows, cols, k)
+    tiles = torch.empty(plan["tile_bytes"] // 4, dtype=torch.int32, device="cuda")
+    scores = torch.empty((rows, k), dtype=torch.float32, device="cuda")
+    ev = {"gram": [], "allreduce": [], "score": []}
+    keep = {}
+
+    def step():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e[0].record(stream)
+        engine.s3_expected_tiles(x, cols, k, tiles=tiles)
+        e[1].record(stream)
+        if world > 1:
+            dist.all_reduce(tiles[: plan["ntiles"] * 128 * 256])
+        e[2].record(stream)
+        counts, exp3 = engine.s3_finalize(tiles, cols, k, plan["mp"], total_bins, want_counts=False, want_exp=True)
+        terms = engine.s3_terms(exp3.reshape(-1), cols, k)
+        e[3].record(stream)
+        engine.scores_s3(x, cols, k, terms, out32=scores)
+        e[4].record(stream)
+        ev["gram"].append((e[0], e[1]))
+        ev["allreduce"].append((e[1], e[2]))
+        ev["score"].append((e[3], e[4]))
+        keep["exp3"] = exp3
+    step()
+    for v in ev.values():
+        v.clear()
+    ms = _timed_loop(torch, dist, world, stream, step, steps)
+    parts = torch.tensor([sum(a.elapsed_time(b) for a, b in ev[n]) / len(ev[n]) for n in ("gram", "allreduce", "score")],
+                         device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(parts, op=dist.ReduceOp.MAX)
+    # closed form: the float32 table sums to 1 and the tile buffer's off-diagonal-block entries to bins C (C-1)
+    total = float(keep["exp3"].double().sum().item())
+    ck = cols * k
+    useful = total_bins * ck * (ck + 1)
+    return {"bins_total": total_bins, "bins_per_gpu": rows, "saliency": 3, "ms_per_step": ms,
+            "value": total_bins / (ms * 1e-3), "unit": "bins/s", "scaling": "strong",
+            "gram_ms": float(parts[0]), "allreduce_ms": float(parts[1]), "score_ms": float(parts[2]),
+            "allreduce_bytes": int(plan["ntiles"]) * 128 * 256 * 4,
+            "gram_useful_TOPS": useful / world / (float(parts[0]) * 1e-3) / 1e12,
+            "check": "ok" if abs(total - 1.0) < 1e-5 else "FAILED: expected table sums to %r" % total}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -256,25 +514,27 @@ def run_ours(args):
     scores = torch.empty((bins, k), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream()
     k1_ev = []
+    plain_step, last = _make_step(torch, dist, engine, world, x, cols, k, saliency, cnt, scores)
 
     def step(timed):
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        engine.bin_counts(x, cols, k, out=cnt)                               # K1
-        if timed:
-            e1.record(stream)
-            k1_ev.append((e0, e1))
-        n1, n2 = engine.expected_tables(cnt, cols, want_s1=saliency == 1, want_s2=saliency == 2)   # K2
+        if not timed:
+            return plain_step()
+        # same launches, with a pair of events around K1 (the kernel of the `roofline` object)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        engine.bin_counts(x, cols, k, out=cnt)
+        e1.record(stream)
+        k1_ev.append((e0, e1))
+        n1, n2 = engine.expected_tables(cnt, cols, want_s1=saliency == 1, want_s2=saliency == 2)
         n = n1 if saliency == 1 else n2
         if world > 1 and not os.environ.get("EPI_BENCH_SKIP_ALLREDUCE"):
-            dist.all_reduce(n)                                               # the path's only exchange
-        e = engine.normalize(n)                                              # K4 (2 kernels)
+            dist.all_reduce(n)
+        e = engine.normalize(n)
         if saliency == 1:
-            engine.scores_s1(cnt, cols, e, out32=scores)                     # K5
+            engine.scores_s1(cnt, cols, e, out32=scores)
         else:
             engine.scores_s2(cnt, cols, e, out32=scores)
-        return e
+        last["n"], last["e"] = n, e
 
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("EPI_BENCH_NO_CLOCKS") else None
     for _ in range(max(3, args.warmup)):
@@ -310,36 +570,26 @@ def run_ours(args):
     ms_per_step = float(elapsed_ms.item()) / args.steps
     value = bins * world / (ms_per_step * 1e-3)
     k1_ms = float(k1_ms.item())
+    check, _ = _check_step(torch, dist, world, last, bins * world, cols, saliency, scores)
+
+    # ---- the north-star target: ONE genome / ONE chr1 sharded over the GPUs (strong scaling), S2, S1 and S3 ----
+    target = None
+    if args.config == "s2_genome_833" and not args.no_target and not args.bins:
+        target = {}
+        for name, fn in (("s2", lambda: _strong_section(torch, dist, engine, world, x, cols, k, 2, GENOME_BINS, args.steps)),
+                         ("s1", lambda: _strong_section(torch, dist, engine, world, x, cols, k, 1, GENOME_BINS, args.steps)),
+                         ("s3_chr1", lambda: _s3_strong_section(torch, dist, engine, synth, world, rank, 1_250_000, cols, k))):
+            try:
+                target[name] = fn()
+            except Exception as exc:
+                target[name] = {"error": str(exc)[:300]}
+                torch.cuda.synchronize()
+            torch.cuda.empty_cache()
 
     # ---- end to end through the host-buffer C-ABI call ----
     e2e = None
     if not args.no_e2e:
-        host = None
-        e2e_bins = bins
-        while host is None and e2e_bins >= 1024:
-            try:
-                host = torch.empty((e2e_bins, x.shape[1]), dtype=torch.int8, pin_memory=True)
-            except RuntimeError:
-                e2e_bins //= 2
-        host.copy_(x[:e2e_bins])
-        torch.cuda.synchronize()
-        engine.single_host(host, cols, k, saliency)                          # warm-up (allocations)
-        if world > 1:
-            dist.barrier()
-        times = []
-        for _ in range(args.e2e_steps):
-            tic = time.perf_counter()
-            engine.single_host(host, cols, k, saliency)
-            times.append(time.perf_counter() - tic)
-        t = torch.tensor([sum(times) / len(times)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ntab = k if saliency == 1 else k * k
-        e2e = {"value": e2e_bins * world / float(t.item()), "unit": "bins/s",
-               "h2d_bytes_per_step": e2e_bins * int(x.shape[1]), "d2h_bytes_per_step": e2e_bins * k * 4 + ntab * 12,
-               "bins_per_gpu": e2e_bins, "steps": args.e2e_steps,
-               "api": "epi_single_host (C ABI, pinned host matrix in, tables + float32 scores out)"}
-        del host
+        e2e = _e2e_section(torch, dist, engine, world, x, bins, cols, k, saliency, args.e2e_steps)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -357,24 +607,65 @@ def run_ours(args):
             "metric": "bins/sec for expected+scores (S%d)" % saliency, "value": value, "unit": "bins/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "bins_per_gpu": bins, "biosamples": cols, "states": k, "saliency": saliency,
-                       "distribution": args.kind, "parallelism": "bins sharded x%d, int64 table allreduce" % world,
-                       "l2": "inputs (%.1f GB/GPU) larger than L2, no flush needed" % (bins * x.shape[1] / 1e9)},
+            "data": "synthetic", "check": check,
+            "config": config_dict(args, world, bins, cols, k, desc, pitch=int(x.shape[1])),
             "roofline": {"bound": "hbm", "kernel": "k1_counts_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bins * cols, "ms_per_launch": k1_ms},
             "step_roofline": {"algorithmic_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                               "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"},
-            "e2e": e2e, "gpu_launches": 6 * args.steps, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP[saliency] * args.steps, "clocks": clocks,
         }
+        if target is not None:
+            line["target"] = target
         if world == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_baseline(cols, k, saliency)
-            line["cpu_baseline"] = base
+            try:
+                line["cpu_baseline"] = cpu_arm(args, 1, 0, budget_s=12.0)[0]
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# our kernels launched per step: K1, K2, K4, then S2: table preparation + tensor-core scores + gated DIRECT fallback;
+# S1: value table + look-up kernel
+LAUNCHES_PER_STEP = {1: 5, 2: 6}
+
+
+def _e2e_section(torch, dist, engine, world, x, bins, cols, k, saliency, steps):
+    """The same metric through epi_single_host (the reference-facing C-ABI call) with the matrix in pinned HOST memory:
+    H2D of the matrix and D2H of tables + scores are inside the timed region."""
+    host = None
+    e2e_bins = bins
+    while host is None and e2e_bins >= 1024:
+        try:
+            host = torch.empty((e2e_bins, x.shape[1]), dtype=torch.int8, pin_memory=True)
+        except RuntimeError:
+            e2e_bins //= 2
+    host.copy_(x[:e2e_bins])
+    torch.cuda.synchronize()
+    engine.single_host(host, cols, k, saliency)                          # warm-up (allocations)
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(steps):
+        tic = time.perf_counter()
+        engine.single_host(host, cols, k, saliency)
+        times.append(time.perf_counter() - tic)
+    mine = sum(times) / len(times)
+    t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ntab = k if saliency == 1 else k * k
+    h2d = e2e_bins * int(x.shape[1])
+    out = {"value": e2e_bins * world / float(t.item()), "unit": "bins/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_bins * k * 4 + ntab * 12,
+           "bins_per_gpu": e2e_bins, "steps": steps, "rank0_h2d_GBps_incl_everything": h2d / mine / 1e9,
+           "api": "epi_single_host (C ABI, pinned host matrix in, tables + float32 scores out)"}
+    del host
+    return out
 
 
 def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, desc):

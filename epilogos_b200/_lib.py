@@ -36,7 +36,7 @@ PROTOTYPES = {
     "epi_shuffled_counts_perm": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64,
                                          c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "epi_shuffled_counts_philox": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_uint64,
-                                           c_int32, c_void_p, c_void_p, c_void_p]),
+                                           c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "epi_pairwise_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                      c_void_p]),
     "epi_quiescent_mask": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p,

@@ -50,11 +50,14 @@ class CudaBackend:
         return torch.as_tensor(array).to(self.device)
 
     # -- float32 scores [rows, K] of the shard
-    def scores(self, cnt, width, saliency, exp, perms=None):
+    def scores(self, cnt, width, saliency, exp, perms=None, exact=False):
+        """`exact`: evaluate the S2 terms one by one with the reference's float64 expression (EPI_SCORE_DIRECT) instead
+        of the tensor-core TABLE form; S1 is exact either way (its value table is built with that expression)."""
         exp = exp.to(self.device).contiguous()
         if saliency == 1:
             return engine.scores_s1(cnt, width, exp)
-        return engine.scores_s2(cnt, width, exp, perms=perms)
+        return engine.scores_s2(cnt, width, exp, perms=perms,
+                                mode=engine.EPI_SCORE_DIRECT if exact else engine.EPI_SCORE_TABLE)
 
     # -- S3 ------------------------------------------------------------------------------------------
     def states_to_device(self, states0):
@@ -80,8 +83,9 @@ class CudaBackend:
         return engine.shuffled_counts_perm(xa, states_a.shape[1], xb, states_b.shape[1], p.contiguous(), num_states,
                                            size_a, size_b)
 
-    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None):
-        oa, ob = engine.shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm, width=width)
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None, bin_offset=0):
+        oa, ob = engine.shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm, width=width,
+                                               bin_offset=bin_offset)
         return (oa[0], ob[0]) if nperm == 1 else (oa, ob)
 
     def pairwise_combine(self, score_a, score_b, null_a, null_b):

@@ -249,9 +249,10 @@ def shuffled_counts_perm(xa, cols_a, xb, cols_b, perm, num_states, size_a, size_
     return ca, cb
 
 
-def shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None):
+def shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None, bin_offset=0):
     """nperm uniform shuffles per bin drawn on the device; returns int16 tensors [nperm, bins, K].
-    `width` = combined number of biosamples (default: size_a + size_b, right unless -g shrinks the groups)."""
+    `width` = combined number of biosamples (default: size_a + size_b, right unless -g shrinks the groups);
+    `bin_offset` = global index of row 0 (the random stream of a bin is keyed by its global index)."""
     _require_cuda(cnt_a, torch.int16, "cnt_a")
     _require_cuda(cnt_b, torch.int16, "cnt_b")
     bins, k = cnt_a.shape
@@ -259,7 +260,7 @@ def shuffled_counts_philox(cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=No
     ob = torch.empty((nperm, bins, k), dtype=torch.int16, device=cnt_a.device)
     _lib.call("epi_shuffled_counts_philox", _ptr(cnt_a), _ptr(cnt_b), bins, k,
               int(width if width is not None else size_a + size_b), int(size_a), int(size_b),
-              ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(nperm), _ptr(oa), _ptr(ob), _stream())
+              ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(bin_offset), int(nperm), _ptr(oa), _ptr(ob), _stream())
     return oa, ob
 
 

@@ -120,9 +120,11 @@ int epi_scores_s3(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch
  *                               permuted by perm[b][0..cols_a+cols_b) (helpers.py:183-194; size = group widths,
  *                               or -g for both).  Bit-exact replay of a seeded reference run.
  *   epi_shuffled_counts_philox  nperm independent uniform shuffles per bin, drawn on the device from the
- *                               group counts as multivariate hypergeometric variates (Philox4x32-10 keyed
- *                               by seed, bin, permutation); `width` = combined biosamples (upper bound of
- *                               a row's label count); outputs are [nperm][bins][K].  The reference draws one.
+ *                               group counts as multivariate hypergeometric variates (float64 inversion, 53-bit
+ *                               uniforms; Philox4x32-10 keyed by seed, GLOBAL bin index = bin_offset + row,
+ *                               permutation: a bin's draw does not depend on how the bins are sharded);
+ *                               `width` = combined biosamples (upper bound of a row's label count); outputs
+ *                               are [nperm][bins][K].  The reference draws one shuffle per bin.
  *   epi_pairwise_combine        delta = score_a - score_b (float32, scores.py:223); null_dist =
  *                               sum_s d^2 * sign(sum_s d), d = null_a - null_b, float32 with numpy's pairwise
  *                               summation order (scores.py:224-232).  Either output (with its inputs) may be NULL.
@@ -134,7 +136,7 @@ int epi_shuffled_counts_perm(const int8_t* xa_dev, int64_t pitch_a, int32_t cols
                              uint16_t* cnt_b_out, void* stream);
 int epi_shuffled_counts_philox(const uint16_t* cnt_a_dev, const uint16_t* cnt_b_dev, int64_t bins,
                                int32_t num_states, int32_t width, int32_t size_a, int32_t size_b, uint64_t seed,
-                               int32_t nperm,
+                               int64_t bin_offset, int32_t nperm,
                                uint16_t* cnt_a_out, uint16_t* cnt_b_out, void* stream);
 int epi_pairwise_combine(const float* score_a, const float* score_b, const float* null_a, const float* null_b,
                          int64_t rows, int32_t num_states, float* delta_out, float* null_dist_out, void* stream);

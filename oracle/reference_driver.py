@@ -1,10 +1,12 @@
 """Drive the UNMODIFIED reference (meuleman/epilogos, /root/reference) on small inputs.
 
-TEST INFRASTRUCTURE ONLY.  This file is the only place that imports the reference.  It exists to
-(1) generate the golden fixtures committed under tests/golden/ (see tests/golden/make_golden.py) and
-(2) cross-check the numpy restatement in oracle/epilogos_oracle.py while authoring.
-/root/reference does not exist on the GPU box, so nothing in tests/, bench.py or smoke() imports this
-module at run time; they use the committed fixtures.
+TEST / BENCHMARK INFRASTRUCTURE ONLY.  This file is the only place that imports the reference.  It exists to
+(1) generate the golden fixtures committed under tests/golden/ (see tests/golden/make_golden.py),
+(2) cross-check the numpy restatement in oracle/epilogos_oracle.py while authoring, and
+(3) time the reference's own CPU path for bench.py's `--impl reference` arm and `cpu_baseline` leg.
+/root/reference does not exist on the GPU box: there the package is imported from the byte-for-byte staged copy
+oracle/_ref/ (oracle/stage_reference.py, git-ignored, travels with the gpurun snapshot).  Nothing in tests/ or smoke()
+imports this module at run time; they use the committed fixtures.
 
 The reference cannot be imported as-is in this image: helpers.py:7 pulls in filter_regions.py which
 imports natsort/pyranges (filter_regions.py:10), and run.py:14 pulls matplotlib/statsmodels.  None of
@@ -18,7 +20,9 @@ from pathlib import Path
 
 import numpy as np
 
-REFERENCE_ROOT = Path("/root/reference")
+from .stage_reference import staged_root
+
+REFERENCE_ROOT = staged_root() or Path("/root/reference")
 
 _STUBS = ["natsort", "pyranges", "matplotlib", "matplotlib.pyplot", "matplotlib.lines", "statsmodels",
           "statsmodels.stats", "statsmodels.stats.multitest", "pysam"]
@@ -225,3 +229,82 @@ def run_simsearch_build(scores_path, window_bins, block_size, window_bp, filter_
             return dict(indices=np.load(out / "simsearch_indices.npy", allow_pickle=True), bed_text=bed,
                         cube_coords=cube_coords, cube_scores=cube_scores, reduced_genome=reduced,
                         leftovers=sorted(p.name for p in out.iterdir()))
+
+
+# ------------------------------------------------------------------------------------------------
+# timing of the reference's own `epilogos -l` compute stages (bench.py --impl reference / cpu_baseline)
+# ------------------------------------------------------------------------------------------------
+def write_matrix_tsv_gz(path, states0, chrom="chr1", bin_size=200, level=1):
+    """Fast writer of the reference's input format (README.md:286-292) for benchmark samples: 0-based int labels ->
+    1-based decimal text, one row per bin, gzip.  Vectorised (the per-row Python writer above takes minutes at
+    100,000 x 833)."""
+    import gzip
+    v = np.asarray(states0).astype(np.int16) + 1
+    rows, cols = v.shape
+    cell = np.empty((rows, cols, 3), dtype=np.uint8)
+    cell[..., 0] = 9                                   # tab
+    cell[..., 1] = 48 + v // 10
+    cell[..., 2] = 48 + v % 10
+    keep = np.ones((rows, cols, 3), dtype=bool)
+    keep[..., 1] = v >= 10                             # no leading zero
+    flat = cell[keep]
+    lens = keep.reshape(rows, -1).sum(axis=1)
+    ends = np.cumsum(lens)
+    with gzip.open(path, "wb", compresslevel=level) as f:
+        lo = 0
+        for r in range(rows):
+            f.write(b"%s\t%d\t%d" % (chrom.encode(), r * bin_size, (r + 1) * bin_size))
+            f.write(flat[lo:ends[r]].tobytes())
+            f.write(b"\n")
+            lo = ends[r]
+
+
+def _parse_verbose_times(text):
+    """Seconds the first worker spent in the compute loops, from the reference's own verbose timers
+    (expected.py:108-114 / 141-160 / 187-202, scores.py:305-324 / 400-423 / 484-506): the `    Time:` line that
+    follows `Calculating expected frequencies...` / `Calculating Scores...`."""
+    total, armed = 0.0, False
+    for line in text.splitlines():
+        if line.startswith("Calculating expected frequencies") or line.startswith("Calculating Scores"):
+            armed = True
+        elif armed and line.strip().startswith("Time:"):
+            try:
+                total += float(line.split("Time:")[1])
+            except ValueError:
+                pass
+            armed = False
+    return total
+
+
+def time_pipeline(file1, file2, num_states, saliency, nproc, workdir, verbose_timers=False):
+    """expected.main -> expectedCombination.main -> scores.main of the unmodified reference on TSV(.gz) input file(s)
+    with `nproc` worker processes (run.py:196/214, 231, 246/268 -- what `epilogos -l -c nproc` runs before the ROI step).
+    Returns (seconds wall clock incl. parse + gz write, seconds of the first worker's compute loops or None)."""
+    import os
+    import time
+    expected_main, combination_main, scores_main = _import_reference()
+    out = Path(workdir) / "out"
+    if out.exists():
+        import shutil
+        shutil.rmtree(out)
+    out.mkdir(parents=True)
+    tag = "bench_s%d" % saliency
+    exp_path = out / ("exp_freq_%s.npy" % tag)
+    log = Path(workdir) / "stdout.log"
+    sys.stdout.flush()
+    saved = os.dup(1)
+    fd = os.open(str(log), os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.dup2(fd, 1)                                    # forked pool workers inherit it: their timers land in the log
+    try:
+        t0 = time.perf_counter()
+        expected_main(file1, file2, num_states, saliency, out, tag, nproc, verbose_timers)
+        combination_main(out, exp_path, tag, verbose_timers)
+        scores_main(file1, file2, num_states, saliency, out, exp_path, tag, nproc, num_states - 1, -1, verbose_timers)
+        sys.stdout.flush()
+        wall = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(fd)
+    compute = _parse_verbose_times(log.read_text()) if verbose_timers else None
+    return wall, compute

@@ -34,7 +34,7 @@ class OracleBackend:
     def to_device(self, array):
         return torch.as_tensor(array)
 
-    def scores(self, cnt, width, saliency, exp, perms=None):
+    def scores(self, cnt, width, saliency, exp, perms=None, exact=False):
         c = self._cnt(cnt)
         if saliency == 1:
             return torch.from_numpy(orc.s1_scores_from_counts(c, width, exp.numpy()))
@@ -46,8 +46,25 @@ class OracleBackend:
         sa, sb = orc.paired_split(states_a, states_b, perm, gs)
         return self.counts(sa, num_states), self.counts(sb, num_states)
 
-    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None):
-        raise NotImplementedError("the test double only replays explicit permutations")
+    def shuffled_counts_device(self, cnt_a, cnt_b, size_a, size_b, seed, nperm=1, width=None, bin_offset=0):
+        """numpy multivariate hypergeometric draws keyed like the device kernel: (seed, permutation, GLOBAL bin)."""
+        a, b = self._cnt(cnt_a), self._cnt(cnt_b)
+        rows, k = a.shape
+        oa = np.zeros((nperm, rows, k), dtype=np.int64)
+        ob = np.zeros_like(oa)
+        for p in range(nperm):
+            for r in range(rows):
+                rng = np.random.default_rng([int(seed) & (2 ** 63 - 1), p, bin_offset + r])
+                comb = a[r] + b[r]
+                na = min(size_a, int(comb.sum()))
+                ga = rng.multivariate_hypergeometric(comb, na) if na else np.zeros(k, dtype=np.int64)
+                rest = comb - ga
+                nb = min(size_b, int(rest.sum()))
+                gb = rng.multivariate_hypergeometric(rest, nb) if nb else np.zeros(k, dtype=np.int64)
+                oa[p, r], ob[p, r] = ga, gb
+        ta = torch.from_numpy(oa.astype(np.uint16).view(np.int16))
+        tb = torch.from_numpy(ob.astype(np.uint16).view(np.int16))
+        return (ta[0], tb[0]) if nperm == 1 else (ta, tb)
 
     def pairwise_combine(self, score_a, score_b, null_a, null_b):
         delta = None if score_a is None else score_a - score_b

@@ -297,6 +297,11 @@ def main():
         paired_case("paired_synth_c30_c25_k18", xa, xb, 18, (1, 2), seed=10)
         paired_case("paired_synth_g20_k18", xa, xb, 18, (1, 2), seed=12, group_size=20)
         paired_case("paired_synth_q0_k18", xa[:400], xb[:400], 18, (1,), seed=13, quiescent_state=-1)
+    if want("paired_gwide"):
+        # -g larger than half the combined width: the second shuffled slice [:, G:2G] is clipped to N - G columns
+        xa = orc.synth_states(400, 30, 18, seed=8)
+        xb = orc.synth_states(400, 25, 18, seed=9)
+        paired_case("paired_synth_g40_k18", xa, xb, 18, (1, 2), seed=14, group_size=40)
     if want("s3big"):
         s3_big_case("synth_s3_c833_k18")
     if want("roi"):

@@ -211,7 +211,8 @@ def run_paired_pipeline(tmp, xa, xb, k, saliency, backend, seed, group_size=-1, 
     return counts, np.load(exp_path), null, quies, text
 
 
-@pytest.mark.parametrize("name", ["paired_real10_k18", "paired_synth_g20_k18", "paired_synth_q0_k18"])
+@pytest.mark.parametrize("name", ["paired_real10_k18", "paired_synth_g20_k18", "paired_synth_q0_k18",
+                                  "paired_synth_g40_k18"])
 def test_paired_pipeline_files_match_reference(tmp_path, golden, name):
     from fake_backend import OracleBackend
     g = golden(name)
@@ -340,3 +341,76 @@ def test_expected_chunk_workers_under_the_reference_names(tmp_path):
     assert n2.dtype == np.int64 and np.array_equal(n2, orc.s2_expected_counts_rowloop(xa[10:50], 18))
     both = np.concatenate((xa, xb), axis=1)
     assert np.array_equal(expected.s2Calc(fa, fb, (0, 60), 18, False, backend=be), orc.s2_expected_counts(both, 18))
+
+
+NPERM_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import torch.distributed as td
+from pathlib import Path
+from fake_backend import OracleBackend
+from epilogos_b200 import pairwise, session
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+pairwise.calculateScoresPairwise(1, Path({fa!r}), Path({fb!r}), 18, Path({out!r}), Path({exp!r}), "t", "m", 17, -1, False,
+                                 backend=OracleBackend(), null_mode="device", seed=4242, nperm=3)
+td.destroy_process_group()
+"""
+
+
+def test_device_null_nperm_rows_are_permutations_and_do_not_depend_on_sharding(tmp_path):
+    """Device-drawn null with nperm > 1: nullDistances is [nperm, rows] with row p = the p-th shuffle of every bin (checked
+    against a direct evaluation of the same keyed draws), and two ranks sharing the rows produce the same array as one
+    rank, because a bin's draw is keyed by (seed, file, permutation, GLOBAL bin index)."""
+    from fake_backend import OracleBackend
+    from epilogos_b200 import pairwise, session
+    from oracle import epilogos_oracle as orc
+    xa = orc.synth_states(37, 9, 18, seed=21)
+    xb = orc.synth_states(37, 6, 18, seed=22)
+    fa, fb = tmp_path / "a.txt", tmp_path / "b.txt"
+    write_tsv(fa, xa); write_tsv(fb, xb)
+    exp = orc.normalize_expected(orc.s1_expected_counts(np.concatenate((xa, xb), axis=1), 18))
+    exp_path = tmp_path / "exp.npy"
+    np.save(exp_path, exp)
+    be = OracleBackend()
+    one = tmp_path / "one"; one.mkdir()
+    session.clear()
+    pairwise.calculateScoresPairwise(1, fa, fb, 18, one, exp_path, "t", "m", 17, -1, False, backend=be,
+                                     null_mode="device", seed=4242, nperm=3)
+    null1 = np.load(one / "temp_nullDistances_t_m.npz")["nullDistances"]
+    assert null1.shape == (3, 37) and null1.dtype == np.float32
+    # direct evaluation of permutation p from the same keyed draws
+    ca, cb = be.counts(xa, 18), be.counts(xb, 18)
+    oa, ob = be.shuffled_counts_device(ca, cb, 9, 6, pairwise.file_seed(4242, "m"), nperm=3, width=15)
+    for p in range(3):
+        na = orc.s1_scores_from_counts(be._cnt(oa[p]), 9, exp)
+        nb = orc.s1_scores_from_counts(be._cnt(ob[p]), 6, exp)
+        d = na - nb
+        want = np.sum(np.square(d), axis=1) * np.sign(np.sum(d, axis=1))
+        assert null1[p].tobytes() == want.astype(np.float32).tobytes()
+    assert not np.array_equal(null1[0], null1[1])
+    # another file name -> another stream
+    other = tmp_path / "other"; other.mkdir()
+    session.clear()
+    pairwise.calculateScoresPairwise(1, fa, fb, 18, other, exp_path, "t", "m2", 17, -1, False, backend=be,
+                                     null_mode="device", seed=4242, nperm=3)
+    assert not np.array_equal(np.load(other / "temp_nullDistances_t_m2.npz")["nullDistances"], null1)
+    # two gloo ranks sharing the rows
+    two = tmp_path / "two"; two.mkdir()
+    port = 33500 + (os.getpid() % 2000)
+    code = NPERM_WORKER.format(root=str(ROOT), tests=str(ROOT / "tests"), port=port, fa=str(fa), fb=str(fb), out=str(two),
+                               exp=str(exp_path))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    logs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    null2 = np.load(two / "temp_nullDistances_t_m.npz")["nullDistances"]
+    assert null2.tobytes() == null1.tobytes()
+    session.clear()
+
+
+def test_shuffled_widths_follow_numpy_slicing():
+    from epilogos_b200.pairwise import shuffled_widths
+    for c1, c2, g in [(30, 25, -1), (30, 25, 20), (30, 25, 40), (30, 25, 55), (30, 25, 70), (5, 5, 5)]:
+        sh = np.zeros((1, c1 + c2))
+        want = (c1, c2) if g == -1 else (sh[:, :g].shape[1], sh[:, g:2 * g].shape[1])
+        assert shuffled_widths(c1, c2, g) == want

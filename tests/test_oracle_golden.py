@@ -73,7 +73,8 @@ def test_s3_tables_and_scores_match_reference(golden, name):
     assert np.array_equal(orc.s3_expected_counts_rowloop(x[:50], k), orc.s3_expected_counts(x[:50], k))
 
 
-PAIRED = ["paired_real10_k18", "paired_synth_c30_c25_k18", "paired_synth_g20_k18", "paired_synth_q0_k18"]
+PAIRED = ["paired_real10_k18", "paired_synth_c30_c25_k18", "paired_synth_g20_k18", "paired_synth_q0_k18",
+          "paired_synth_g40_k18"]
 
 
 @pytest.mark.parametrize("name", PAIRED)
