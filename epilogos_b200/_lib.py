@@ -25,6 +25,7 @@ PROTOTYPES = {
     "epi_scores_s1": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "epi_scores_s2": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
                               c_void_p]),
+    "epi_scores_s2_fixed_point": (c_int, [c_void_p, c_int32, c_int64, c_void_p, POINTER(c_int32), c_void_p]),
     "epi_s3_plan": (c_int, [c_int64, c_int32, c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
                             POINTER(c_int64), POINTER(c_int64)]),
     "epi_s3_onehot": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_int64, c_int64, c_void_p]),

@@ -48,6 +48,12 @@ int launch_k2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t* n
 int scores_s2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
                  float* o32, double* o64, cudaStream_t st);
 bool scores_s2_tc_eligible(int width);
+// kind::f16 form of the S2 score mat-vec (tc_scores_h.cu): counts as fp16 subnormals, width <= 1023
+int scores_s2_h(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
+                float* o32, double* o64, cudaStream_t st);
+bool scores_s2_h_eligible(int width);
+int scores_s2_h_fixed_point(const float* e, int K, int64_t perms, unsigned long long* mfix_dev, int* fbits_host,
+                            cudaStream_t st);
 
 // ---- device-side PTX wrappers -----------------------------------------------------------------
 #ifdef __CUDACC__

@@ -141,11 +141,14 @@ __global__ void k5_s1_table_kernel(const float* __restrict__ exp1, int K, int wi
     }
 }
 
-template <bool SMEM_TABLE>
-__global__ void __launch_bounds__(K5_THREADS) k5_s1_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
-                                                           int width, const float* __restrict__ v32g,
-                                                           const double* __restrict__ v64g,
-                                                           float* __restrict__ out32, double* __restrict__ out64) {
+// THREADS: 256, or 1024 when the value table is large: the table is per CTA, so one big CTA keeps 32 warps resident on an SM
+// where 256-thread CTAs with a 60 KB table each would only fit twice (16 warps; measured 0.52 ms -> see profiles/).
+template <bool SMEM_TABLE, int THREADS>
+__global__ void __launch_bounds__(THREADS) k5_s1_kernel(const uint16_t* __restrict__ cnt, long long bins, int K,
+                                                        int width, const float* __restrict__ v32g,
+                                                        const double* __restrict__ v64g,
+                                                        float* __restrict__ out32, double* __restrict__ out64) {
+    constexpr int K5_THREADS = THREADS, K5_WARPS = THREADS / 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint16_t* cslab = reinterpret_cast<uint16_t*>(smem_raw);                          // K5_WARPS * 2 * 32 * K u16
     float* fslab = reinterpret_cast<float*>(smem_raw + K5_WARPS * 32 * K * 4);        // K5_WARPS * 32 * K f32
@@ -346,14 +349,21 @@ static int launch_s1(const uint16_t* cnt, int64_t bins, int K, int width, const 
     const size_t base = (size_t)K5_WARPS * 32 * K * 8 + K5_WARPS * 16;
     const size_t table = (size_t)n * 4;
     const int64_t ntiles = (bins + K5_THREADS - 1) / K5_THREADS;
-    if (table <= (size_t)S1_SMEM_TABLE_BYTES) {
-        auto kern = k5_s1_kernel<true>;
+    const size_t base_big = (size_t)32 * 32 * K * 8 + 32 * 16;          // 1024-thread CTA
+    if (table <= (size_t)S1_SMEM_TABLE_BYTES && 4 * (base + table + 1024) > (size_t)220 * 1024 &&
+        base_big + table + 1024 <= (size_t)226 * 1024 && getenv("EPI_K5_S1_SMALL_CTA") == nullptr) {
+        // fewer than four 256-thread CTAs would fit next to their tables: one 1024-thread CTA per SM shares ONE table
+        auto kern = k5_s1_kernel<true, 1024>;
+        EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base_big + table)));
+        kern<<<persistent_grid((bins + 1023) / 1024, 1), 1024, base_big + table, st>>>(cnt, bins, K, width, v32, v64, o32, o64);
+    } else if (table <= (size_t)S1_SMEM_TABLE_BYTES) {
+        auto kern = k5_s1_kernel<true, K5_THREADS>;
         EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + table)));
         const int per_sm = (int)((size_t)220 * 1024 / (base + table + 1024));
         kern<<<persistent_grid(ntiles, k5_ctas_per_sm(per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm))), K5_THREADS, base + table, st>>>(
             cnt, bins, K, width, v32, v64, o32, o64);
     } else {
-        auto kern = k5_s1_kernel<false>;
+        auto kern = k5_s1_kernel<false, K5_THREADS>;
         EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
         kern<<<persistent_grid(ntiles, k5_ctas_per_sm(4)), K5_THREADS, base, st>>>(cnt, bins, K, width, v32, v64, o32, o64);
     }
@@ -416,6 +426,19 @@ extern "C" int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t K, i
     EPI_REQUIRE(out32_dev == nullptr || (reinterpret_cast<uintptr_t>(out32_dev) & 15) == 0,
                 "out32_dev must be 16-byte aligned");
     return launch_s1(cnt_dev, bins, K, width, exp1_dev, mode == EPI_SCORE_DIRECT, out32_dev, out64_dev, st);
+}
+
+extern "C" int epi_scores_s2_fixed_point(const float* exp2_dev, int32_t K, int64_t perms, uint64_t* mfix_dev,
+                                         int32_t* fraction_bits_out, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (check_device()) return 3;
+    EPI_REQUIRE(K >= 1 && K <= EPI_MAX_STATES, "num_states=%d out of range [1, %d]", K, EPI_MAX_STATES);
+    EPI_REQUIRE(perms >= 1 && exp2_dev != nullptr && mfix_dev != nullptr, "bad argument");
+    int fbits = 0;
+    if (int rc = scores_s2_h_fixed_point(exp2_dev, K, perms, reinterpret_cast<unsigned long long*>(mfix_dev), &fbits, st))
+        return rc;
+    if (fraction_bits_out) *fraction_bits_out = fbits;
+    return 0;
 }
 
 extern "C" int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t K, int32_t width, int64_t perms,

@@ -529,6 +529,8 @@ static int launch_k5_tc(const uint16_t* cnt, int64_t bins, int K, int width, int
 // the expected table has a zero entry; the caller queues the DIRECT kernel behind it, gated on that flag.
 int scores_s2_tc(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const float* e, int* zero_flag,
                  float* o32, double* o64, cudaStream_t st) {
+    // EPI_K5_F16=1 and width <= 1023: the kind::f16 form of this kernel (tc_scores_h.cu), kept for A/B runs
+    if (scores_s2_h_eligible(width)) return scores_s2_h(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K == 18) return launch_k5_tc<18, 18, 3>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K == 15) return launch_k5_tc<16, 15, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);
     if (K <= 16) return launch_k5_tc<16, 0, 4>(cnt, bins, K, width, perms, e, zero_flag, o32, o64, st);

@@ -104,6 +104,15 @@ def scores_s2(cnt, width, exp2, perms=None, want64=False, mode=EPI_SCORE_TABLE, 
     return (out32, out64) if want64 else out32
 
 
+def scores_s2_fixed_point(exp2, num_states, perms):
+    """(M int64 tensor [K, K] on the device, F): the fixed-point image of -log2 E2 used by the tensor-core S2 scores."""
+    _require_cuda(exp2, torch.float32, "exp2")
+    m = torch.empty((num_states, num_states), dtype=torch.int64, device=exp2.device)
+    f = ctypes.c_int32(0)
+    _lib.call("epi_scores_s2_fixed_point", _ptr(exp2), int(num_states), int(perms), _ptr(m), ctypes.byref(f), _stream())
+    return m, f.value
+
+
 _pinned_scores = {}
 
 

@@ -78,6 +78,13 @@ int epi_scores_s1(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int
                   const float* exp1_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream);
 int epi_scores_s2(const uint16_t* cnt_dev, int64_t bins, int32_t num_states, int32_t width, int64_t perms,
                   const float* exp2_dev, float* out32_dev, double* out64_dev, int32_t mode, void* stream);
+/* Diagnostic: the fixed-point image M[s][t] = round(-log2 E2[s][t] * 2^F) (uint64 [K][K], device) that the tensor-core
+ * kind::f16 form of the TABLE evaluation of epi_scores_s2 (EPI_K5_F16=1, width <= 1023: 55-bit, five 11-bit fp16
+ * digits) multiplies the counts with, and F.
+ * With EPI_K5_DEBUG=1 / 2 in the environment, the float64 output of that kernel is replaced by the low / high part of
+ * the integer sum_s c_s M[s][t] = L + 2^33 H exactly as assembled from the tensor-core accumulators (exactness tests). */
+int epi_scores_s2_fixed_point(const float* exp2_dev, int32_t num_states, int64_t perms, uint64_t* mfix_dev,
+                              int32_t* fraction_bits_out, void* stream);
 
 /* ---- K3: S3 expected counts (expected.py:165-204, s3Calc) as an int8 one-hot Gram matrix ------------
  * N3[i][j][a][c] = #{ b : x[b][i]==a and x[b][j]==c } for i != j, 0 for i == j  (int32 per worker in the

@@ -396,6 +396,50 @@ def test_s3_stage_drivers(eng, golden, tmp_path):
     assert np.max(np.abs(npz["scoreArr"] - g["s3_scores"])) < 2e-2
 
 
+def test_k5_tensor_core_matvec_is_exact(eng, monkeypatch):
+    """The S2 score kernel multiplies the count rows (uint16 counts read as fp16 SUBNORMALS) with the 11-bit digits of the
+    55-bit fixed-point image of -log2 E on the tensor cores (kind::f16, fp32 accumulators) and relies on that product being
+    EXACT integer arithmetic.  With EPI_K5_DEBUG=1 / 2 the kernel returns the two halves L, H of sum_s c_s M_st as assembled
+    from the accumulators; both must equal integer arithmetic on the same fixed-point table, for random, sparse and extreme
+    count rows (all 1023 labels in one state, counts 0 / 1 / 1023) and 18-, 15- and 7-state models."""
+    for k, width, seed in ((18, 833, 1), (15, 127, 2), (18, 1023, 3), (7, 500, 4), (16, 1000, 5)):
+        rng = np.random.default_rng(seed)
+        bins = 3000
+        # count rows that sum to `width`: multinomial with random sparsity, plus extremes
+        p = rng.dirichlet(np.full(k, 0.3), size=bins)
+        cnt = np.stack([rng.multinomial(width, pi) for pi in p]).astype(np.int64)
+        cnt[0] = 0; cnt[0, 0] = width
+        cnt[1] = 0; cnt[1, k - 1] = width
+        cnt[2] = 0; cnt[2, : 2] = (1, width - 1)
+        e = rng.random((k, k)).astype(np.float64) ** 4 + 1e-9
+        e = (e / e.sum()).astype(np.float32)
+        ed = torch.from_numpy(e).cuda()
+        perms = width * (width - 1)
+        m, fbits = eng.scores_s2_fixed_point(ed, k, perms)
+        m = m.cpu().numpy().astype(np.int64)
+        assert 40 <= fbits <= 54 and m.min() >= 0 and m.max() < 2 ** 55
+        want = np.rint(np.ldexp(-np.log2(e.astype(np.float64)), fbits))
+        assert np.abs(m - want).max() <= 16                      # device log2 vs numpy log2: an ulp or two of a 53-bit value
+        monkeypatch.setenv("EPI_K5_F16", "1")                   # the kind::f16 kernel (opt-in)
+        digits = [(m >> (11 * d)) & 2047 for d in range(5)]      # [5][K][K]
+        n = [cnt @ dg for dg in digits]                          # N_d[b][t] = sum_s c_bs digit_d(M_st): exact in int64
+        want_l = n[0] + (n[1] << 11) + (n[2] << 22)
+        want_h = n[3] + (n[4] << 11)
+        cd = torch.from_numpy(cnt.astype(np.uint16).view(np.int16)).cuda()
+        for dbg, ref in ((1, want_l), (2, want_h)):
+            monkeypatch.setenv("EPI_K5_DEBUG", str(dbg))
+            _, got = eng.scores_s2(cd, width, ed, perms=perms, want64=True)
+            assert np.array_equal(got.cpu().numpy(), ref.astype(np.float64)), (k, width, dbg)
+        monkeypatch.delenv("EPI_K5_DEBUG")
+        # and the scores themselves, against the oracle, with both tensor-core kernels (kind::f16 default, kind::i8)
+        ref64 = orc.s2_scores_from_counts(cnt, perms, e, dtype=np.float64)
+        _, s64 = eng.scores_s2(cd, width, ed, perms=perms, want64=True)
+        np.testing.assert_allclose(s64.cpu().numpy(), ref64, rtol=RTOL, atol=ATOL)
+        monkeypatch.delenv("EPI_K5_F16")
+        _, s64b = eng.scores_s2(cd, width, ed, perms=perms, want64=True)
+        np.testing.assert_allclose(s64b.cpu().numpy(), ref64, rtol=RTOL, atol=ATOL)
+
+
 # ------------------------------------------------------------------------------------------------ paired
 @pytest.mark.parametrize("k", [5, 8, 15, 18, 25])
 def test_pairwise_combine_is_bitwise_numpy(eng, k):
@@ -573,6 +617,9 @@ def test_device_null_distances_have_the_reference_distribution(eng, golden, name
         ref_null.append(r["null_distances"])
     ref_null = np.concatenate(ref_null)
     ks = stats.ks_2samp(dev_null, ref_null)
+    print("KS statistic %.4f, p = %.3f; 1%% / 99%% quantiles device %.3f / %.3f, reference %.3f / %.3f" % (
+        ks.statistic, ks.pvalue, np.quantile(dev_null, 0.01), np.quantile(dev_null, 0.99), np.quantile(ref_null, 0.01),
+        np.quantile(ref_null, 0.99)))
     assert ks.pvalue > 1e-3, "KS statistic %.4f, p = %.2e" % (ks.statistic, ks.pvalue)
     assert abs(np.mean(dev_null) - np.mean(ref_null)) < 4 * np.std(ref_null) / np.sqrt(ref_null.size) * 2 + 1e-9
     for q in (0.001, 0.01, 0.99, 0.999):        # tails that feed the p-values downstream
