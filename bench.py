@@ -141,6 +141,8 @@ def reference_cpu_arm(args, steps, warmup, budget_s):
         b = max((t2 - t1) / (n2 - n1), 1e-7)
         a = max(t1 - b * n1, 0.0)
         n = int(max(n2, min(bins_full, 400_000, (per_step - a) / b)))
+        if saliency == 3:           # the fixed set-up (tens of seconds) would leave no rows at all: time at least 32 rows per worker
+            n = max(n, nproc * 32)
         n = max(nproc, n // nproc * nproc)
         f1, f2 = _sample_files(d, args.config, n, cols, k, args.kind)
         times, compute = [], []
@@ -635,8 +637,25 @@ LAUNCHES_PER_STEP = {1: 5, 2: 6}
 
 
 def _e2e_section(torch, dist, engine, world, x, bins, cols, k, saliency, steps):
-    """The same metric through epi_single_host (the reference-facing C-ABI call) with the matrix in pinned HOST memory:
-    H2D of the matrix and D2H of tables + scores are inside the timed region."""
+    """The same metric through the reference-facing C-ABI calls with the matrix in pinned HOST memory: H2D of the matrix and
+    D2H of tables + scores are inside the timed region.  Headline: epi_single_host_packed -- the host buffer is the
+    bit-packed transport layout the packer produces (5 bits per label for 18 states, 4 for <= 16), expanded on the device;
+    `int8_layout` is epi_single_host on the plain int8 matrix of the same rows."""
+    def timed(fn):
+        fn()                                                                 # warm-up (allocations)
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(steps):
+            tic = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - tic)
+        mine = sum(times) / len(times)
+        t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return mine, float(t.item())
+
     host = None
     e2e_bins = bins
     while host is None and e2e_bins >= 1024:
@@ -645,26 +664,24 @@ def _e2e_section(torch, dist, engine, world, x, bins, cols, k, saliency, steps):
         except RuntimeError:
             e2e_bins //= 2
     host.copy_(x[:e2e_bins])
+    packed_dev, bits = engine.pack_bits(x[:e2e_bins], cols, k)
+    packed = torch.empty(packed_dev.shape, dtype=torch.uint8, pin_memory=True)
+    packed.copy_(packed_dev)
+    del packed_dev
     torch.cuda.synchronize()
-    engine.single_host(host, cols, k, saliency)                          # warm-up (allocations)
-    if world > 1:
-        dist.barrier()
-    times = []
-    for _ in range(steps):
-        tic = time.perf_counter()
-        engine.single_host(host, cols, k, saliency)
-        times.append(time.perf_counter() - tic)
-    mine = sum(times) / len(times)
-    t = torch.tensor([mine], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ntab = k if saliency == 1 else k * k
-    h2d = e2e_bins * int(x.shape[1])
-    out = {"value": e2e_bins * world / float(t.item()), "unit": "bins/s",
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_bins * k * 4 + ntab * 12,
-           "bins_per_gpu": e2e_bins, "steps": steps, "rank0_h2d_GBps_incl_everything": h2d / mine / 1e9,
-           "api": "epi_single_host (C ABI, pinned host matrix in, tables + float32 scores out)"}
-    del host
+    d2h = e2e_bins * k * 4 + ntab * 12
+    mine_p, t_p = timed(lambda: engine.single_host_packed(packed, cols, k, saliency, bits))
+    mine_i, t_i = timed(lambda: engine.single_host(host, cols, k, saliency))
+    h2d_p, h2d_i = e2e_bins * int(packed.shape[1]), e2e_bins * int(x.shape[1])
+    out = {"value": e2e_bins * world / t_p, "unit": "bins/s", "h2d_bytes_per_step": h2d_p, "d2h_bytes_per_step": d2h,
+           "bins_per_gpu": e2e_bins, "steps": steps, "rank0_pcie_GBps": (h2d_p + d2h) / mine_p / 1e9,
+           "api": "epi_single_host_packed (C ABI: pinned host matrix in the %d-bit packed transport layout in, tables + "
+                  "float32 scores out)" % bits,
+           "int8_layout": {"value": e2e_bins * world / t_i, "unit": "bins/s", "h2d_bytes_per_step": h2d_i,
+                           "d2h_bytes_per_step": d2h, "rank0_pcie_GBps": (h2d_i + d2h) / mine_i / 1e9,
+                           "api": "epi_single_host (int8 host matrix)"}}
+    del host, packed
     return out
 
 
@@ -715,6 +732,28 @@ def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, de
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step, gram_ms = float(ms[0]), float(ms[1])
+    e2e = None
+    if not args.no_e2e:
+        # end to end through epi_s3_host: pinned host matrix in, float32 scores out (the 0.9 GB table stays on the device)
+        host = torch.empty(x.shape, dtype=torch.int8, pin_memory=True)
+        host.copy_(x)
+        out = torch.empty((bins, k), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize()
+        engine.s3_host(host, cols, k, want_exp=False, scores_out=out)
+        if world > 1:
+            dist.barrier()
+        times = []
+        for _ in range(2):
+            tic = time.perf_counter()
+            engine.s3_host(host, cols, k, want_exp=False, scores_out=out)
+            times.append(time.perf_counter() - tic)
+        t = torch.tensor([sum(times) / len(times)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": bins * world / float(t.item()), "unit": "bins/s", "h2d_bytes_per_step": bins * int(x.shape[1]),
+               "d2h_bytes_per_step": bins * k * 4, "steps": 2,
+               "api": "epi_s3_host (C ABI: pinned int8 host matrix in, float32 scores out; each rank its own matrix)"}
+        del host, out
     if rank == 0:
         ck = cols * k
         useful = bins * ck * (ck + 1)
@@ -737,9 +776,14 @@ def run_ours_s3(args, engine, synth, dist, world, rank, local, bins, cols, k, de
                          "achieved": useful / (gram_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "TOP/s",
                          "frac": useful / (gram_ms * 1e-3) / 1e12 / peak_tops, "traffic": None, "peak_source": src,
                          "algorithmic_ops_per_launch": useful, "ms_per_launch": gram_ms},
-            "e2e": None, "gpu_launches": steps * (2 * ((bins + engine.S3_CHUNK_BINS - 1) // engine.S3_CHUNK_BINS) + 4),
+            "e2e": e2e, "gpu_launches": steps * (2 * ((bins + engine.S3_CHUNK_BINS - 1) // engine.S3_CHUNK_BINS) + 4),
             "clocks": clocks,
         }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_arm(args, 1, 0, budget_s=20.0)[0]
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -799,6 +843,40 @@ def run_ours_paired(args, engine, synth, dist, world, rank, local, bins, cols, k
     ms = torch.tensor([t0.elapsed_time(t1) / steps], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    e2e = None
+    if not args.no_e2e:
+        # end to end through epi_paired_host with pinned host matrices: tables, delta, quiescence mask and null distances
+        # come back to the host.  Headline: ONE null shuffle per bin (what the reference computes); p1000 = the north-star
+        # extension (1000 shuffles per bin, 4 bytes x 1000 per bin of null distances cross PCIe).
+        ha = torch.empty(xa.shape, dtype=torch.int8, pin_memory=True)
+        hb = torch.empty(xb.shape, dtype=torch.int8, pin_memory=True)
+        ha.copy_(xa)
+        hb.copy_(xb)
+        delta_out = torch.empty((bins, k), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize()
+        res = {}
+        for p in (1, nperm):
+            null_out = torch.empty((p, bins), dtype=torch.float32, pin_memory=True)
+            call = lambda: engine.paired_host(ha, c1, hb, c2, k, 1, k - 1, seed=7, nperm=p, null_out=null_out,
+                                              delta_out=delta_out)
+            call()
+            if world > 1:
+                dist.barrier()
+            times = []
+            for _ in range(2):
+                tic = time.perf_counter()
+                call()
+                times.append(time.perf_counter() - tic)
+            t = torch.tensor([sum(times) / len(times)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[p] = {"value": bins * world / float(t.item()), "unit": "bins/s",
+                      "h2d_bytes_per_step": bins * int(xa.shape[1] + xb.shape[1]),
+                      "d2h_bytes_per_step": bins * (k * 4 + 1 + 4 * p) + k * 12, "null_permutations": p, "steps": 2}
+            del null_out
+        e2e = dict(res[1], api="epi_paired_host (C ABI: two pinned int8 host matrices in; table, delta, quiescence mask and "
+                               "null distances out), one null shuffle per bin as in the reference", p1000=res[nperm])
+        del ha, hb, delta_out
     if rank == 0:
         ms_per_step = float(ms[0])
         line = {
@@ -808,8 +886,13 @@ def run_ours_paired(args, engine, synth, dist, world, rank, local, bins, cols, k
             "dtype": "int64+f64", "data": "synthetic",
             "config": {"workload": desc, "bins_per_gpu": bins, "group_sizes": [c1, c2], "states": k, "saliency": 1,
                        "null_permutations": nperm, "bin_permutation_pairs_per_s": bins * world * nperm / (ms_per_step * 1e-3)},
-            "roofline": None, "e2e": None, "gpu_launches": steps * (12 + (nperm // batch) * 6), "clocks": clocks,
+            "roofline": None, "e2e": e2e, "gpu_launches": steps * (12 + (nperm // batch) * 6), "clocks": clocks,
         }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_arm(args, 1, 0, budget_s=12.0)[0]
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -66,6 +66,16 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, POINTER(c_int32)]),
     "epi_pairwise_real_reduce": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "epi_single_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "epi_packed_bits": (c_int, [c_int32]),
+    "epi_packed_pitch": (c_int64, [c_int32, c_int32]),
+    "epi_pack_states_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_int64, c_int32]),
+    "epi_pack_states": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_int64, c_void_p]),
+    "epi_unpack_states": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p, c_int64, c_void_p]),
+    "epi_single_host_packed": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                       c_void_p]),
+    "epi_s3_host": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
+    "epi_paired_host": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32,
+                                c_int32, c_uint64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -151,6 +151,104 @@ def single_host(x_host, cols, num_states, saliency, want_scores=True, scores_out
     return counts, exp, scores
 
 
+# ------------------------------------------------------------------------------------------------ packed transport layout
+def packed_bits(num_states):
+    return int(_lib.load().epi_packed_bits(int(num_states)))
+
+
+def packed_pitch(cols, bits):
+    return int(_lib.load().epi_packed_pitch(int(cols), int(bits)))
+
+
+def pack_bits_host(x_host, cols, num_states, out=None, threads=0):
+    """int8 host matrix [bins, pitch] (numpy or CPU torch tensor) -> bit-packed host matrix uint8 [bins, packed_pitch]
+    (pinned when a GPU is present), 4 bits per label for <= 16 states, else 5.  Runs on CPU threads; no GPU needed."""
+    if isinstance(x_host, torch.Tensor):
+        xp, (bins, pitch) = ctypes.c_void_p(x_host.data_ptr()), x_host.shape
+    else:
+        x_host = np.ascontiguousarray(x_host, dtype=np.int8)
+        xp, (bins, pitch) = ctypes.c_void_p(x_host.ctypes.data), x_host.shape
+    bits = packed_bits(num_states)
+    pp = packed_pitch(cols, bits)
+    if out is None:
+        out = torch.empty((bins, pp), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    _lib.call("epi_pack_states_host", xp, bins, int(cols), pitch, bits, ctypes.c_void_p(out.data_ptr()), pp, int(threads))
+    return out, bits
+
+
+def pack_bits(x, cols, num_states):
+    """Device int8 [bins, pitch] -> device packed uint8 [bins, packed_pitch]."""
+    _require_cuda(x, torch.int8, "x")
+    bits = packed_bits(num_states)
+    pp = packed_pitch(cols, bits)
+    out = torch.empty((x.shape[0], pp), dtype=torch.uint8, device=x.device)
+    _lib.call("epi_pack_states", _ptr(x), x.shape[0], int(cols), x.shape[1], bits, _ptr(out), pp, _stream())
+    return out, bits
+
+
+def unpack_bits(packed, cols, bits):
+    """Device packed uint8 [bins, packed_pitch] -> device int8 [bins, pitch_for(cols)] (pad bytes beyond the last group
+    of 8 labels are not written)."""
+    _require_cuda(packed, torch.uint8, "packed")
+    out = torch.zeros((packed.shape[0], pitch_for(cols)), dtype=torch.int8, device=packed.device)
+    _lib.call("epi_unpack_states", _ptr(packed), packed.shape[0], int(cols), int(bits), packed.shape[1], _ptr(out),
+              out.shape[1], _stream())
+    return out
+
+
+def single_host_packed(packed_host, cols, num_states, saliency, bits, want_scores=True, scores_out=None):
+    """single_host with the matrix in the bit-packed transport layout (CPU uint8 tensor [bins, packed_pitch])."""
+    if packed_host.is_cuda or packed_host.dtype != torch.uint8 or not packed_host.is_contiguous():
+        raise TypeError("packed_host must be a contiguous CPU uint8 tensor")
+    bins, pp = packed_host.shape
+    shape = (num_states,) if saliency == 1 else (num_states, num_states)
+    counts = np.empty(shape, dtype=np.int64)
+    exp = np.empty(shape, dtype=np.float32)
+    scores, sp = None, ctypes.c_void_p(0)
+    if want_scores:
+        if scores_out is None:
+            key = (bins, num_states)
+            if key not in _pinned_scores:
+                _pinned_scores.clear()
+                _pinned_scores[key] = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
+            scores_out = _pinned_scores[key]
+        scores, sp = scores_out.numpy(), ctypes.c_void_p(scores_out.data_ptr())
+    _lib.call("epi_single_host_packed", ctypes.c_void_p(packed_host.data_ptr()), bins, int(cols), pp, int(bits),
+              int(num_states), int(saliency), ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(exp.ctypes.data), sp)
+    return counts, exp, scores
+
+
+def s3_host(x_host, cols, num_states, want_exp=True, scores_out=None):
+    """Whole S3 path on a HOST matrix (CPU int8 torch tensor [bins, pitch]): (exp float32 [C,C,K,K] or None, scores)."""
+    bins, pitch = x_host.shape
+    exp = np.empty((cols, cols, num_states, num_states), dtype=np.float32) if want_exp else None
+    if scores_out is None:
+        scores_out = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
+    _lib.call("epi_s3_host", ctypes.c_void_p(x_host.data_ptr()), bins, int(cols), pitch, int(num_states),
+              ctypes.c_void_p(exp.ctypes.data if want_exp else 0), ctypes.c_void_p(scores_out.data_ptr()))
+    return exp, scores_out.numpy()
+
+
+def paired_host(xa_host, cols_a, xb_host, cols_b, num_states, saliency, quiescent_state, group_size=-1, seed=0,
+                bin_offset=0, nperm=1, null_out=None, delta_out=None):
+    """Paired mode on HOST matrices (CPU int8 torch tensors).  Returns dict(counts, exp, delta, null [nperm, bins], quiescent)."""
+    bins = xa_host.shape[0]
+    shape = (num_states,) if saliency == 1 else (num_states, num_states)
+    counts = np.empty(shape, dtype=np.int64)
+    exp = np.empty(shape, dtype=np.float32)
+    if delta_out is None:
+        delta_out = torch.empty((bins, num_states), dtype=torch.float32, pin_memory=True)
+    if null_out is None:
+        null_out = torch.empty((max(nperm, 1), bins), dtype=torch.float32, pin_memory=True)
+    quies = np.empty(bins, dtype=np.uint8)
+    _lib.call("epi_paired_host", ctypes.c_void_p(xa_host.data_ptr()), xa_host.shape[1], int(cols_a),
+              ctypes.c_void_p(xb_host.data_ptr()), xb_host.shape[1], int(cols_b), bins, int(num_states), int(saliency),
+              int(quiescent_state), int(group_size), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(bin_offset), int(nperm),
+              ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(exp.ctypes.data), ctypes.c_void_p(delta_out.data_ptr()),
+              ctypes.c_void_p(null_out.data_ptr() if nperm > 0 else 0), ctypes.c_void_p(quies.ctypes.data))
+    return dict(counts=counts, exp=exp, delta=delta_out.numpy(), null=null_out.numpy()[:nperm], quiescent=quies.astype(bool))
+
+
 def device_info():
     sm, major, minor = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
     _lib.call("epi_device_info", ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))

@@ -167,6 +167,45 @@ int epi_pairwise_real_reduce(const float* delta_dev, int64_t rows, int32_t num_s
 int epi_single_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states,
                     int32_t saliency, int64_t* counts_host, float* exp_host, float* scores_host);
 
+/* ---- bit-packed transport layout of the state matrix (csrc/packbits.cu) ----------------------------
+ * The kernels compute on the int8 matrix, but a label carries 5 bits (4 for <= 16 states) and epi_single_host is bound by
+ * the PCIe copy of the matrix.  The packed layout is what the reader side can hand over instead: a row is
+ * ceil(cols / 8) groups of 8 labels in `bits` bytes (label j in bits [bits*j, bits*(j+1)) of the little-endian group),
+ * rows packed_pitch bytes apart (epi_packed_pitch: a multiple of 16).
+ *   epi_packed_bits / epi_packed_pitch   bits for a state model, row pitch for a width
+ *   epi_pack_states_host                 int8 host matrix -> packed host matrix (CPU threads; threads <= 0: all cores)
+ *   epi_pack_states / epi_unpack_states  the same conversion on the device, both directions
+ *   epi_single_host_packed               epi_single_host with the matrix in the packed layout: packed chunks cross PCIe and
+ *                                        are expanded on the device right before the count kernel (helpers.py:150-160 hands
+ *                                        the reference an int64 array; this is the narrowest exact form of the same labels) */
+int epi_packed_bits(int32_t num_states);
+int64_t epi_packed_pitch(int32_t cols, int32_t bits);
+int epi_pack_states_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pitch, int32_t bits,
+                         uint8_t* packed_host, int64_t packed_pitch, int32_t threads);
+int epi_pack_states(const int8_t* x_dev, int64_t bins, int32_t cols, int64_t pitch, int32_t bits, uint8_t* packed_dev,
+                    int64_t packed_pitch, void* stream);
+int epi_unpack_states(const uint8_t* packed_dev, int64_t bins, int32_t cols, int32_t bits, int64_t packed_pitch,
+                      int8_t* x_dev, int64_t pitch, void* stream);
+int epi_single_host_packed(const uint8_t* packed_host, int64_t bins, int32_t cols, int64_t packed_pitch, int32_t bits,
+                           int32_t num_states, int32_t saliency, int64_t* counts_host, float* exp_host, float* scores_host);
+
+/* ---- S3 and paired mode with HOST buffers ----------------------------------------------------------
+ * epi_s3_host      expected.main (S3) -> expectedCombination.main -> scores.main (S3) for one in-memory matrix
+ *                  (expected.py:165-204, expectedCombination.py:42, scores.py:455-506): exp_host float32 [C][C][K][K] or
+ *                  NULL, scores_host float32 [bins][K] or NULL.
+ * epi_paired_host  calculateScoresPairwise for one pair of in-memory matrices (scores.py:172-256): expected table of the
+ *                  union [A | B] (helpers.py:173-179), delta = score(A) - score(B), quiescence mask, and nperm
+ *                  device-drawn null shuffles per bin (the reference draws one) with their signed squared distances.
+ *                  group_size -1 = the groups' own widths, else -g (clipped like the reference's slices, helpers.py:190-194);
+ *                  bin_offset = global index of row 0 (keys the random streams).  Outputs (any may be NULL): counts int64 /
+ *                  exp float32 [K] or [K][K], delta float32 [bins][K], null float32 [nperm][bins], quiescent uint8 [bins]. */
+int epi_s3_host(const int8_t* x_host, int64_t bins, int32_t cols, int64_t pitch, int32_t num_states, float* exp_host,
+                float* scores_host);
+int epi_paired_host(const int8_t* xa_host, int64_t pitch_a, int32_t cols_a, const int8_t* xb_host, int64_t pitch_b,
+                    int32_t cols_b, int64_t bins, int32_t num_states, int32_t saliency, int32_t quiescent_state,
+                    int32_t group_size, uint64_t seed, int64_t bin_offset, int32_t nperm, int64_t* counts_host,
+                    float* exp_host, float* delta_host, float* null_host, uint8_t* quiescent_host);
+
 /* ---- host-side I/O either side of the kernels (no GPU needed) -------------------------------------
  * epi_tsv_shape       rows = number of newline characters (helpers.countRows, helpers.py:80-99), cols = biosample
  *                     columns of the first line (fields - 3).  Plain or gzip files.

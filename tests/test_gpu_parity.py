@@ -88,6 +88,67 @@ def test_bad_arguments_raise(eng):
         eng.bin_counts(x, 17, 18)
 
 
+@pytest.mark.parametrize("bins,cols,k", [(1, 1, 2), (37, 833, 18), (1000, 127, 15), (4097, 833, 18), (300, 8, 16),
+                                         (129, 17, 32), (515, 1000, 25)])
+def test_packed_transport_layout_round_trip(eng, bins, cols, k):
+    """Bit-packed transport layout: device pack == host pack; device unpack restores every label; counts of the unpacked
+    matrix equal the oracle's (the pad bytes the unpack kernel leaves unwritten are never interpreted)."""
+    rng = np.random.default_rng(bins + cols)
+    x = rng.integers(0, k, size=(bins, cols)).astype(np.int8)
+    xh = eng.pack_states(x, pin=False)
+    host_packed, bits = eng.pack_bits_host(xh, cols, k)
+    dev_packed, bits2 = eng.pack_bits(xh.cuda(), cols, k)
+    assert bits == bits2 and torch.equal(dev_packed.cpu(), host_packed.cpu())
+    back = eng.unpack_bits(host_packed.cuda(), cols, bits)
+    assert torch.equal(back[:, :cols].cpu(), torch.from_numpy(x))
+    got = eng.counts_to_numpy(eng.bin_counts(back, cols, k))
+    assert np.array_equal(got.astype(np.int64), orc.bin_counts(x, k))
+
+
+@pytest.mark.parametrize("cols,k,saliency", [(833, 18, 2), (833, 18, 1), (127, 15, 2)])
+def test_single_host_packed_equals_single_host(eng, cols, k, saliency):
+    """epi_single_host_packed (packed chunks over PCIe, expanded on the device) == epi_single_host, bit for bit, over
+    several H2D chunks."""
+    x = orc.synth_states(600_000 if cols < 200 else 300_000, cols, k, seed=3)
+    xh = eng.pack_states(x)
+    packed, bits = eng.pack_bits_host(xh, cols, k)
+    c0, e0, s0 = eng.single_host(xh, cols, k, saliency)
+    s0 = s0.copy()
+    c1, e1, s1 = eng.single_host_packed(packed, cols, k, saliency, bits)
+    assert np.array_equal(c0, c1) and e0.tobytes() == e1.tobytes() and s0.tobytes() == s1.tobytes()
+    ref = orc.s1_expected_counts(x, k) if saliency == 1 else orc.s2_expected_counts(x, k)
+    assert np.array_equal(c1, ref)
+
+
+def test_s3_and_paired_host_entry_points(eng, golden):
+    """epi_s3_host / epi_paired_host (host matrices in, host results out) against the reference goldens."""
+    g = golden("synth_s3_c40_k18")
+    x, k = g["x"], int(g["num_states"])
+    exp, scores = eng.s3_host(eng.pack_states(x), x.shape[1], k)
+    assert exp.tobytes() == g["s3_exp"].tobytes()
+    assert np.max(np.abs(scores - g["s3_scores"])) < 2e-2
+    np.testing.assert_allclose(scores, orc.s3_scores_f64(x, k, g["s3_exp"]).astype(np.float32), rtol=1e-5, atol=1e-6)
+    for name in ("paired_synth_c30_c25_k18", "paired_synth_g20_k18"):
+        g = golden(name)
+        xa, xb, k, gs, q = g["xa"], g["xb"], int(g["num_states"]), int(g["group_size"]), int(g["quiescent_state"])
+        for s in (1, 2):
+            r = eng.paired_host(eng.pack_states(xa), xa.shape[1], eng.pack_states(xb), xb.shape[1], k, s, q, group_size=gs,
+                                seed=5, nperm=3)
+            assert np.array_equal(r["counts"], g["s%d_counts" % s]) and r["exp"].tobytes() == g["s%d_exp" % s].tobytes()
+            assert np.array_equal(r["quiescent"], g["s%d_quiescence" % s])
+            perm = orc.reference_shuffle_indices(int(g["seed"]), xa.shape[0], xa.shape[1] + xb.shape[1])
+            ref = orc.paired_scores(xa, xb, perm, k, s, g["s%d_exp" % s], q, gs)
+            if s == 1:
+                assert r["delta"].tobytes() == ref["delta"].tobytes()         # exact value table
+            else:                                                             # TABLE mode: rare 1-ulp differences of a score
+                np.testing.assert_allclose(r["delta"], ref["delta"], rtol=0, atol=2e-7)
+                assert (r["delta"] == ref["delta"]).mean() > 0.995
+            assert r["null"].shape == (3, xa.shape[0]) and np.isfinite(r["null"]).all()
+            assert not np.array_equal(r["null"][0], r["null"][1])
+            # same distribution as the replayed reference shuffle (coarse: medians and spread)
+            assert abs(np.median(r["null"]) - np.median(ref["null_distances"])) < 0.5 * np.std(ref["null_distances"])
+
+
 # ------------------------------------------------------------------------------------ K2 / K4 / K5
 SINGLE = ["real10_chr1_k18", "real10_chr1_k18_nproc3", "synth_c833_k18", "synth_uniform_c833_k18", "synth_c127_k15"]
 
@@ -622,8 +683,8 @@ def test_device_null_distances_have_the_reference_distribution(eng, golden, name
         np.quantile(ref_null, 0.99)))
     assert ks.pvalue > 1e-3, "KS statistic %.4f, p = %.2e" % (ks.statistic, ks.pvalue)
     assert abs(np.mean(dev_null) - np.mean(ref_null)) < 4 * np.std(ref_null) / np.sqrt(ref_null.size) * 2 + 1e-9
-    for q in (0.001, 0.01, 0.99, 0.999):        # tails that feed the p-values downstream
-        assert abs(np.quantile(dev_null, q) - np.quantile(ref_null, q)) < 0.25 * np.std(ref_null) + 1e-9
+    for q, tol in ((0.01, 0.5), (0.05, 0.25), (0.95, 0.25), (0.99, 0.5)):      # the tails feed the p-values downstream
+        assert abs(np.quantile(dev_null, q) - np.quantile(ref_null, q)) < tol * np.std(ref_null) + 1e-9
 
 
 def test_paired_stage_driver_device_null(eng, golden, tmp_path):

@@ -253,3 +253,33 @@ def test_native_inflate_reads_the_writers_multi_member_files_across_blocks(tmp_p
     monkeypatch.delenv("EPI_ZLIB_INFLATE", raising=False)
     _, got = helpers.read_scores(p)
     assert got.shape == (rows, k) and np.array_equal(got[::997], np.array([[float("%.5f" % float(v)) for v in r] for r in sc[::997]]))
+
+
+def _pack_reference(x, cols, bits):
+    """Label j of a group of 8 in bits [bits*j, bits*(j+1)) of the little-endian group; rows padded to 16 bytes."""
+    bins = x.shape[0]
+    groups = (cols + 7) // 8
+    lab = np.zeros((bins, groups * 8), dtype=np.uint64)
+    lab[:, :cols] = x[:, :cols].astype(np.uint8)
+    v = np.zeros((bins, groups), dtype=np.uint64)
+    for j in range(8):
+        v |= lab[:, j::8] << np.uint64(bits * j)
+    out = np.zeros((bins, (groups * bits + 15) // 16 * 16), dtype=np.uint8)
+    for b in range(bits):
+        out[:, b:groups * bits:bits] = ((v >> np.uint64(8 * b)) & np.uint64(255)).astype(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("cols,k", [(833, 18), (127, 15), (8, 16), (1, 2), (17, 32), (1000, 25)])
+def test_host_packer_layout(cols, k):
+    """epi_pack_states_host (CPU threads, no GPU): the bit-packed transport layout of the state matrix, 4 bits per label
+    for <= 16 states, else 5, against a numpy restatement of the layout; pad bytes of the int8 rows are ignored."""
+    from epilogos_b200 import engine
+    rng = np.random.default_rng(cols * 100 + k)
+    bins = 531
+    x = np.full((bins, engine.pitch_for(cols)), 77, dtype=np.int8)           # garbage in the pad columns
+    x[:, :cols] = rng.integers(0, k, size=(bins, cols))
+    packed, bits = engine.pack_bits_host(x, cols, k, threads=3)
+    assert bits == (4 if k <= 16 else 5)
+    assert packed.shape == (bins, engine.packed_pitch(cols, bits))
+    assert np.array_equal(packed.numpy(), _pack_reference(x, cols, bits))
