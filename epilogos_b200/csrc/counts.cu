@@ -136,14 +136,16 @@ __device__ __forceinline__ void fold_groups(const ChunkSrc<BV, MODE>& src, uint3
     Reduce<4, sizeof...(G), NP>::run(carries, p);
 }
 
-template <int BV, int MODE, int NP>
+// SW: the row is a 128-byte TMA SWIZZLE_128B row (16-byte chunk v lives at chunk v ^ swz) that holds only BV - 1 vectors;
+// the last vector of the chunk is a virtual all-zero vector (label 0, removed again through npad).
+template <int BV, int MODE, int NP, bool SW = false>
 __device__ __forceinline__ void process_chunk(const uint4* __restrict__ row, uint32_t (&p)[NP], uint32_t& sum1,
-                                              uint32_t& sum2, uint32_t one) {
+                                              uint32_t& sum2, uint32_t one, int swz = 0) {
     ChunkSrc<BV, MODE> src;
     src.one = one;
 #pragma unroll
     for (int v = 0; v < BV; ++v) {
-        const uint4 q = row[v];
+        const uint4 q = SW ? (v < BV - 1 ? row[v ^ swz] : make_uint4(0u, 0u, 0u, 0u)) : row[v];
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -173,15 +175,21 @@ __device__ __forceinline__ void flush_planes(uint32_t (&p)[NP], uint32_t (&acc)[
     }
 }
 
-template <int BV, int MODE>
+// SMALL (rows of at most 128 bytes, one chunk of BV = 9 vectors, two-bit modes): the box is 128 bytes wide and written by
+// the TMA unit with SWIZZLE_128B (conflict-free LDS.128 without the odd-pitch padding vector, which becomes virtual), and
+// six counter planes suffice (at most 48 summed words per bin), which shortens the plane flush by a third.  For a 127-column
+// matrix the per-bin fixed work (flush, unpack, staging) is as large as the per-byte work, so both count.
+template <int BV, int MODE, bool SMALL = false>
 __global__ void __launch_bounds__(K1_THREADS, (BV <= 9 ? 3 : 2))
 k1_counts_kernel(const __grid_constant__ CUtensorMap tmap, long long bins, int nchunks, int flush_chunks, int npad,
                  int num_states, int stages, uint32_t one, uint16_t* __restrict__ cnt) {
-    constexpr int NP = PlaneCount<MODE>::N;
+    constexpr int NP = SMALL ? 6 : PlaneCount<MODE>::N;
     constexpr int NACC = (MODE == MODE_B1) ? 16 : 8;
-    constexpr int STAGE_BYTES = BV * 16 * K1_ROWS;
+    constexpr int STAGE_BYTES = (SMALL ? 8 : BV) * 16 * K1_ROWS;
+    static_assert(!SMALL || (BV == 9 && MODE != MODE_B1), "the small-row variant is the one-chunk, two-bit-field case");
 
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw_k1[];
+    uint8_t* smem = SMALL ? smem_raw_k1 + ((1024u - (smem_u32(smem_raw_k1) & 1023u)) & 1023u) : smem_raw_k1;
     uint8_t* ring = smem;
     uint16_t* out_stage = reinterpret_cast<uint16_t*>(smem + (size_t)stages * STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES +
@@ -239,8 +247,8 @@ k1_counts_kernel(const __grid_constant__ CUtensorMap tmap, long long bins, int n
 
         for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&full[s], ph);
-            const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)s * STAGE_BYTES + tid * (BV * 16));
-            process_chunk<BV, MODE, NP>(row, p, sum1, sum2, one);
+            const uint4* row = reinterpret_cast<const uint4*>(ring + (size_t)s * STAGE_BYTES + tid * ((SMALL ? 8 : BV) * 16));
+            process_chunk<BV, MODE, NP, SMALL>(row, p, sum1, sum2, one, tid & 7);
             __syncwarp();
             // p[0] is the XOR of every one-hot word of the chunk: it exists only after all of the chunk's loads returned
             if (lane == 0) mbar_arrive_after(&empty[s], p[0]);
@@ -321,6 +329,7 @@ struct K1Plan {
     int nchunks;
     int mode;
     int npad;
+    bool small;      // one 128-byte swizzled box per row (see k1_counts_kernel)
 };
 
 static K1Plan plan_k1(int cols, int num_states) {
@@ -340,23 +349,25 @@ static K1Plan plan_k1(int cols, int num_states) {
     pl.nchunks = (nvec + best - 1) / best;
     pl.mode = num_states <= 16 ? MODE_F2 : (num_states <= 18 ? MODE_F2M : MODE_B1);
     pl.npad = pl.nchunks * best * 16 - cols;
+    pl.small = best == 9 && nvec <= 8 && pl.mode != MODE_B1 && getenv("EPI_K1_NO_SMALL") == nullptr;
     return pl;
 }
 
-template <int BV, int MODE>
+template <int BV, int MODE, bool SMALL = false>
 static int launch_k1(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, int num_states, uint16_t* cnt,
                           cudaStream_t stream) {
-    constexpr int stage_bytes = BV * 16 * K1_ROWS;
+    constexpr int stage_bytes = (SMALL ? 8 : BV) * 16 * K1_ROWS;
     int stages = (BV <= 3) ? 8 : (BV <= 9 ? 4 : 3);           // measured on B200 at 833 biosamples (tools/k1_sweep.py): 4 stages x 2 CTAs/SM: 2.22 ms;
                                               // 3 x 2: 2.26, 5 x 2: 2.26, 3 x 3: 2.32, 2 x 4: 2.35, 6 x 1: 2.79
-    int ctas_per_sm = (BV <= 3) ? 3 : 2;
+    int ctas_per_sm = (BV <= 3 || SMALL) ? 3 : 2;           // small rows (127 x 15): 0.470 / 0.438 / 0.465 ms at 2 / 3 / 4 CTAs per SM
     if (const char* e = getenv("EPI_K1_STAGES")) stages = atoi(e) > 0 ? atoi(e) : stages;      // tuning knobs
     if (const char* e = getenv("EPI_K1_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;
-    const size_t smem = (size_t)stages * stage_bytes + ((K1_ROWS * num_states * 2 + 15) & ~15) + 2 * stages * 8;
-    auto kern = k1_counts_kernel<BV, MODE>;
+    const size_t smem = (size_t)stages * stage_bytes + ((K1_ROWS * num_states * 2 + 15) & ~15) + 2 * stages * 8 +
+                        (SMALL ? 1024 : 0);
+    auto kern = k1_counts_kernel<BV, MODE, SMALL>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int words_per_chunk = (MODE == MODE_B1) ? 16 * BV : 16 * BV / 3;
-    int flush_chunks = PlaneCount<MODE>::CAP / words_per_chunk;
+    int flush_chunks = (SMALL ? 63 : PlaneCount<MODE>::CAP) / words_per_chunk;
     if (flush_chunks < 1) flush_chunks = 1;
     const int64_t ntiles = (bins + K1_ROWS - 1) / K1_ROWS;
     int64_t grid = (int64_t)sm_count() * ctas_per_sm;
@@ -370,6 +381,12 @@ static int launch_k1(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, in
 template <int BV>
 static int dispatch_mode(const CUtensorMap& tmap, int64_t bins, const K1Plan& pl, int num_states, uint16_t* cnt,
                          cudaStream_t stream) {
+    if constexpr (BV == 9) {
+        if (pl.small) {
+            if (pl.mode == MODE_F2) return launch_k1<9, MODE_F2, true>(tmap, bins, pl, num_states, cnt, stream);
+            return launch_k1<9, MODE_F2M, true>(tmap, bins, pl, num_states, cnt, stream);
+        }
+    }
     switch (pl.mode) {
         case MODE_F2: return launch_k1<BV, MODE_F2>(tmap, bins, pl, num_states, cnt, stream);
         case MODE_F2M: return launch_k1<BV, MODE_F2M>(tmap, bins, pl, num_states, cnt, stream);
@@ -385,11 +402,11 @@ int bin_counts_aligned(const int8_t* x, int64_t bins, int32_t cols, int64_t pitc
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)bins};
     const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
-    const cuuint32_t box[2] = {(cuuint32_t)(pl.bv * 16), (cuuint32_t)K1_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)(pl.small ? 128 : pl.bv * 16), (cuuint32_t)K1_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(x), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, pl.small ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EPI_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (cols=%d bins=%lld pitch=%lld)",
                 (int)r, cols, (long long)bins, (long long)pitch);
     switch (pl.bv) {

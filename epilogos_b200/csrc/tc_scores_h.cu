@@ -383,6 +383,7 @@ template <int KT, int KR, int NWG, bool WANT64>
 static int launch_k5_h2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const uint8_t* ws, float* o32,
                         double* o64, cudaStream_t st) {
     constexpr int NPAD = h5_npad(KT);
+    if (int rc = apply_wait_hint(st)) return rc;
     auto kern = k5_s2_h_kernel<KT, KR, NWG, WANT64>;
     const size_t smem = 1024 + (size_t)NWG * H5_A_BYTES + (size_t)NPAD * 128 + (size_t)NWG * 2 * H5_BINS * K * 2 +
                         (size_t)NWG * H5_BINS * K * 4 + (size_t)(width + 2) * 16 +

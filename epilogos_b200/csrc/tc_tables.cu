@@ -164,6 +164,7 @@ template <int KT, int KR>
 static int launch_k2_tc_impl(const uint16_t* cnt, int64_t bins, int K, int64_t* n1, int64_t* n2, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)T2_OPS * T2_OP_BYTES + (size_t)T2_STAGES * T2_BINS * K * 2 +
                         (2 * T2_STAGES + 2 * T2_OPS + 2) * 8 + 16;
+    if (int rc = apply_wait_hint(st)) return rc;
     auto kern = k2_tc_kernel<KT, KR>;
     EPI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ntiles = (bins + T2_BINS - 1) / T2_BINS;
@@ -500,6 +501,7 @@ template <int KT, int KR, int NWG, bool WANT64>
 static int launch_k5_tc2(const uint16_t* cnt, int64_t bins, int K, int width, int64_t perms, const uint8_t* ws, float* o32,
                          double* o64, cudaStream_t st) {
     constexpr int NPAD = ((8 * KT + 31) / 32) * 32;
+    if (int rc = apply_wait_hint(st)) return rc;
     auto kern = k5_s2_tc_kernel<KT, KR, NWG, WANT64>;
     const size_t smem = 1024 + (size_t)NWG * T5_A_BYTES + (size_t)NPAD * 128 + (size_t)NWG * 2 * T5_BINS * K * 2 +
                         (size_t)NWG * T5_BINS * K * 4 + (size_t)(width + 2) * 16 +

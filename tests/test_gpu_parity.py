@@ -51,6 +51,8 @@ def assert_f32_close(got32, ref32, max_ulp_frac=2e-3):
     (1, 1, 2), (5, 15, 3), (31, 16, 15), (33, 17, 16), (127, 48, 17), (129, 49, 18), (300, 143, 18),
     (257, 144, 18), (1000, 145, 25), (700, 833, 18), (515, 833, 15), (260, 127, 15), (130, 1000, 18),
     (140, 2100, 18), (150, 1700, 16), (135, 1100, 32), (4096, 10, 18), (10000, 833, 18),
+    # rows of 97..128 bytes: the one-box, 128-byte-swizzled variant of the count kernel (two-bit modes only)
+    (300, 128, 16), (500, 100, 18), (77, 113, 15), (1000, 120, 17), (129, 97, 2), (5000, 127, 15), (333, 128, 25),
 ])
 def test_bin_counts_match_oracle(eng, bins, cols, k):
     rng = np.random.default_rng(bins * 7919 + cols * 31 + k)
