@@ -53,9 +53,22 @@ __device__ __forceinline__ void load_count_row(const uint16_t* row, int K, uint3
 #pragma unroll
         for (int i = 0; i < KT / 2; ++i) cw[i] = i < KR / 2 ? w[i] : 0u;
     } else if constexpr (KR != 0) {
+        // odd row length (15 states: 30-byte rows): the row starts on a 4-byte boundary only for even bins.  Read the
+        // (KR + 1) / 2 aligned words that cover it and realign with funnel shifts: 8 LDS.32 + 8 SHF instead of 15 LDS.U16
+        // + their merges (the halfword loads also bank-conflict at this pitch).
+        constexpr int NW = (KR + 1) / 2;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (a & 2) ? 16u : 0u;
+        uint32_t t[NW];
 #pragma unroll
-        for (int i = 0; i < KT / 2; ++i)
-            cw[i] = (2 * i < KR ? (uint32_t)row[2 * i] : 0u) | ((2 * i + 1 < KR ? (uint32_t)row[2 * i + 1] : 0u) << 16);
+        for (int i = 0; i < NW; ++i) t[i] = w[i];
+#pragma unroll
+        for (int i = 0; i < KT / 2; ++i) {
+            if (i < NW - 1) cw[i] = __funnelshift_r(t[i], t[i + 1], sh);
+            else if (i == NW - 1) cw[i] = (sh ? (t[i] >> 16) : t[i]) & 0xffffu;      // last state + nothing
+            else cw[i] = 0u;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < KT / 2; ++i)

@@ -16,6 +16,8 @@
 //  * epi_s3_finalize turns the (all-reduced) tile buffer into the reference's [C][C][K][K] table: int64 counts
 //                    and/or float32 frequencies (float64 divide by the grand total, expectedCombination.py:42),
 //                    mirroring the lower triangle and zeroing the i == j blocks.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -33,49 +35,53 @@ constexpr int G_B_BYTES = G_TN * G_TK;          // 32 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_MAX_GROUPS = 64;
 
+// The Gram matrix is cut into 256 x 256 blocks (Mi, nj), Mi <= nj (on or above the diagonal); block p of the schedule is
+// stored as TWO 128 x 256 tiles t = 2p (rows 256 Mi .. +127) and t = 2p + 1 (rows 256 Mi + 128 .. +255): the unit of the
+// one-CTA kernel is a tile, the unit of the two-CTA kernel a block (each CTA of the pair owns one of its tiles).
 struct TileSchedule {
-    int mt, nt;                       // number of 128-row / 256-col tiles
+    int mt, nt;                       // number of 128-row tiles / 256-col blocks per side
     int ngroups;
-    int total;                        // tiles on or above the diagonal
-    int group_count[G_MAX_GROUPS];    // tiles per raster group
+    int total;                        // tiles on or above the diagonal = 2 x blocks
+    int group_count[G_MAX_GROUPS];    // blocks per raster group
 };
 
-// tile (mi, nj) is needed iff some element has row <= col: mi*128 <= nj*256 + 255  <=>  mi <= 2*nj + 1
-__host__ __device__ inline int tiles_in_group(int mt, int nt, int g) {
+__host__ __device__ inline int blocks_in_group(int nt, int g) {
     const int nj0 = g * G_GROUP;
     const int width = (nt - nj0) < G_GROUP ? (nt - nj0) : G_GROUP;
     int count = 0;
-    for (int w = 0; w < width; ++w) {
-        const int rows = 2 * (nj0 + w) + 2;
-        count += rows < mt ? rows : mt;
-    }
+    for (int w = 0; w < width; ++w) count += nj0 + w + 1;          // rows Mi = 0 .. nj
     return count;
 }
 
-// linear index within the schedule -> (mi, nj); row-major inside a group so that consecutive tiles share A rows
-__device__ inline void decode_tile(const TileSchedule& sc, int t, int& mi, int& nj) {
+// block index within the schedule -> (Mi, nj); row-major inside a group of G_GROUP block columns so that consecutive blocks
+// share A rows and the blocks in flight share operand panels in L2
+__device__ inline void decode_block(const TileSchedule& sc, int p, int& Mi, int& nj) {
     int g = 0;
-    while (g < sc.ngroups - 1 && t >= sc.group_count[g]) {
-        t -= sc.group_count[g];
+    while (g < sc.ngroups - 1 && p >= sc.group_count[g]) {
+        p -= sc.group_count[g];
         ++g;
     }
     const int nj0 = g * G_GROUP;
     const int width = (sc.nt - nj0) < G_GROUP ? (sc.nt - nj0) : G_GROUP;
-    for (int row = 0; row < sc.mt; ++row) {
-        // valid columns of this row inside the group: nj >= ceil((row - 1) / 2)
-        int first = row <= 1 ? 0 : (row - 1 + 1) / 2;
-        first = first > nj0 ? first - nj0 : 0;
+    for (int row = 0; row < sc.nt; ++row) {
+        const int first = row > nj0 ? row - nj0 : 0;             // valid columns of this row inside the group: nj >= row
         const int valid = width - first;
         if (valid <= 0) break;
-        if (t < valid) {
-            mi = row;
-            nj = nj0 + first + t;
+        if (p < valid) {
+            Mi = row;
+            nj = nj0 + first + p;
             return;
         }
-        t -= valid;
+        p -= valid;
     }
-    mi = 0;
+    Mi = 0;
     nj = nj0;      // unreachable for a consistent schedule
+}
+
+__device__ inline void decode_tile(const TileSchedule& sc, int t, int& mi, int& nj) {
+    int Mi;
+    decode_block(sc, t >> 1, Mi, nj);
+    mi = 2 * Mi + (t & 1);
 }
 
 constexpr uint32_t G_IDESC = umma_i8_idesc(G_TM, G_TN);
@@ -255,6 +261,207 @@ s3_gram_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ================================================================================================
+// Gram kernel, two-CTA form (default): a CTA pair (cluster of 2 = one TPC) computes one 256 x 256 block with
+// tcgen05.mma.cta_group::2 (UMMA 256 x 256 x 32).  CTA r of the pair stages rows 256 Mi + 128 r .. +127 of the A operand
+// and rows 256 nj + 128 r .. +127 of the B operand -- 32 KB per 128-bin stage instead of the 48 KB (128 A rows + 256 B
+// rows) of the one-CTA kernel, whose 3.2 POP/s were bound by operand delivery from L2 (94 B/clk/SM at tensor peak), not by
+// the tensor pipe (the same kernel with operand loads disabled issues 4.47 POP/s).  Two 256-column accumulators per CTA
+// (all 512 TMEM columns) let the epilogue of block p overlap the MMAs of block p + 1.
+//   warp 0: TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
+//   warp 1: TMEM allocator (both CTAs) + single-thread MMA issuer (leader CTA only; commits are multicast to both CTAs)
+//   warps 2-5: epilogue, each CTA drains its own 128 accumulator rows into its tile of the block
+// ================================================================================================
+constexpr int G2_STAGES = 6;
+constexpr int G2_HALF_BYTES = 128 * G_TK;               // 128 rows x 128 bins = 16 KB
+constexpr int G2_STAGE_BYTES = 2 * G2_HALF_BYTES;       // A half + B half per CTA
+constexpr uint32_t G2_PEER_MASK = 0xFEFFFFFFu;          // shared::cluster address of the same offset in CTA 0 of the pair
+constexpr uint32_t G2_IDESC = umma_i8_idesc(256, 256);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA 0 of the pair (works from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & G2_PEER_MASK) : "memory");
+}
+// 2D tiled TMA load whose completion bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar) & G2_PEER_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// mbarriers at this offset in BOTH CTAs arrive once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
+s3_gram2_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ TileSchedule sched, int kblocks,
+                int accumulate, int probe, int32_t* __restrict__ tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ring = smem;                                                             // G2_STAGES * 32 KB
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);  // TMA (both CTAs) -> MMA, leader's copy
+    uint64_t* empty = full + G2_STAGES;                                               // MMA -> TMA, one copy per CTA
+    uint64_t* tmem_full = empty + G2_STAGES;                                          // [2] MMA -> epilogue, one copy per CTA
+    uint64_t* tmem_empty = tmem_full + 2;                                             // [2] epilogues of both CTAs -> MMA, leader's copy
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int nblocks = sched.total >> 1;
+    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full[s], 2);            // the leader's expect_tx arrive + the peer producer's arrive
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);      // four epilogue warps of each CTA
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 512);        // two 256-column accumulators x 128 lanes in each CTA
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer (both CTAs) ------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&map);
+            int s = 0;
+            uint32_t ph = 0;
+            long long issued = 0;
+            for (int p = first; p < nblocks; p += stride) {
+                int Mi, nj;
+                decode_block(sched, p, Mi, nj);
+                const int a_row = (2 * Mi + (int)rank) * 128, b_row = nj * 256 + (int)rank * 128;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait_spin_wd(&empty[s], ph ^ 1);
+                    const bool load = !(probe && issued >= G2_STAGES);
+                    if (leader) {
+                        if (load) mbar_expect_tx(&full[s], 2 * G2_STAGE_BYTES);
+                        else mbar_arrive(&full[s]);
+                    } else {
+                        mbar_arrive_leader(&full[s]);
+                    }
+                    if (load) {
+                        uint8_t* st = ring + s * G2_STAGE_BYTES;
+                        tma_load_2d_2sm(st, &map, kb * G_TK, a_row, &full[s]);
+                        tma_load_2d_2sm(st + G2_HALF_BYTES, &map, kb * G_TK, b_row, &full[s]);
+                    }
+                    ++issued;
+                    if (++s == G2_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer (one thread of the leader CTA) ------------------------------
+        if (lane == 0 && leader) {
+            int s = 0, acc = 0;
+            uint32_t ph = 0, acc_ph[2] = {0u, 0u};
+            for (int p = first; p < nblocks; p += stride) {
+                mbar_wait_spin_wd(&tmem_empty[acc], acc_ph[acc] ^ 1);        // both CTAs have drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait_spin_wd(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + s * G2_STAGE_BYTES);
+                    const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(a_addr + G2_HALF_BYTES);
+#pragma unroll
+                    for (int k = 0; k < G_TK / G_UK; ++k)
+                        umma2_i8(d, a_desc + 2 * k, b_desc + 2 * k, G2_IDESC, (kb | k) != 0 ? 1u : 0u);
+                    umma2_commit_both(&empty[s]);             // the stage may be refilled in both CTAs
+                    if (++s == G2_STAGES) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma2_commit_both(&tmem_full[acc]);           // accumulator complete, in both CTAs
+                acc_ph[acc] ^= 1;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------ epilogue: own 128 accumulator rows -> own tile of the block ------------------------------
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_ph[2] = {0u, 0u};
+        for (int p = first; p < nblocks; p += stride) {
+            mbar_wait_spin_wd(&tmem_full[acc], acc_ph[acc]);
+            acc_ph[acc] ^= 1;
+            tc_fence_after();
+            const long long t = 2ll * p + rank;
+            int32_t* dst = tiles + t * (G_TM * G_TN) + (long long)(quarter * 32 + lane) * G_TN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < G_TN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                int4* d4 = reinterpret_cast<int4*>(dst + c0);
+                if (accumulate) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        int4 o = d4[i];
+                        o.x += (int)v[4 * i];
+                        o.y += (int)v[4 * i + 1];
+                        o.z += (int)v[4 * i + 2];
+                        o.w += (int)v[4 * i + 3];
+                        d4[i] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        d4[i] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            acc ^= 1;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
+// ================================================================================================
 // finalise: tile buffer -> [C][C][K][K] int64 counts and / or float32 frequencies
 // one thread per output element (i, j, a, c); reads G[min][max] from the tile that holds it
 // ================================================================================================
@@ -304,8 +511,8 @@ static TileSchedule make_schedule(int64_t mp) {
     sc.ngroups = (sc.nt + G_GROUP - 1) / G_GROUP;
     sc.total = 0;
     for (int g = 0; g < sc.ngroups; ++g) {
-        sc.group_count[g] = tiles_in_group(sc.mt, sc.nt, g);
-        sc.total += sc.group_count[g];
+        sc.group_count[g] = blocks_in_group(sc.nt, g);
+        sc.total += 2 * sc.group_count[g];
     }
     return sc;
 }
@@ -370,6 +577,19 @@ extern "C" int epi_s3_gram(const int8_t* oht_dev, int64_t mp, int64_t bp, int32_
     EPI_REQUIRE(oht_dev != nullptr && tiles_dev != nullptr, "null pointer argument");
     EPI_REQUIRE((reinterpret_cast<uintptr_t>(tiles_dev) & 15) == 0, "tiles_dev must be 16-byte aligned");
     const TileSchedule sc = make_schedule(mp);
+    const int probe2 = (accumulate & 2) ? 1 : 0;
+    if (getenv("EPI_S3_GRAM1") == nullptr) {
+        // two-CTA kernel: one tensor map with 128-row boxes serves the A and the B halves
+        CUtensorMap map;
+        if (int rc = make_oht_map(&map, oht_dev, mp, bp, 128)) return rc;
+        const size_t smem2 = (size_t)G2_STAGES * G2_STAGE_BYTES + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
+        EPI_CUDA(cudaFuncSetAttribute(s3_gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        int grid2 = sm_count() & ~1;
+        if (grid2 > sc.total) grid2 = sc.total;              // total is even: two CTAs per block
+        s3_gram2_kernel<<<grid2, G_THREADS, smem2, st>>>(map, sc, (int)(bp / G_TK), accumulate & 1, probe2, tiles_dev);
+        EPI_CUDA(cudaGetLastError());
+        return 0;
+    }
     CUtensorMap map_a, map_b;
     if (int rc = make_oht_map(&map_a, oht_dev, mp, bp, G_TM)) return rc;
     if (int rc = make_oht_map(&map_b, oht_dev, mp, bp, G_TN)) return rc;
