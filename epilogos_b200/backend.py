@@ -8,7 +8,7 @@ sharding / all-reduce / gather / file-naming logic with a stand-in defined under
 import numpy as np
 import torch
 
-from . import engine
+from . import engine, timing
 
 
 class CudaBackend:
@@ -24,6 +24,10 @@ class CudaBackend:
     def _upload(self, states0):
         """numpy int8 [rows, C] -> device [rows, pitch].  Matrices that come from helpers.read_matrix are views of an
         already pitched (and possibly pinned) buffer and are uploaded as they are."""
+        with timing.stage("host -> device", sync_cuda=True):
+            return self._upload_impl(states0)
+
+    def _upload_impl(self, states0):
         base = getattr(states0, "base", None)
         if (isinstance(base, np.ndarray) and base.dtype == np.int8 and base.ndim == 2 and base.flags.c_contiguous
                 and base.shape[0] == states0.shape[0] and base.shape[1] % 16 == 0 and base.shape[1] >= states0.shape[1]
@@ -32,7 +36,9 @@ class CudaBackend:
         return engine.pack_states(states0).to(self.device, non_blocking=True)
 
     def counts(self, states0, num_states):
-        return engine.bin_counts(self._upload(states0), states0.shape[1], num_states)
+        x = self._upload(states0)
+        with timing.stage("kernels", sync_cuda=True):
+            return engine.bin_counts(x, states0.shape[1], num_states)
 
     def add_counts(self, cnt_a, cnt_b):
         """Counts of the concatenated matrix [A | B] (helpers.py:173-179) = sum of the group counts."""
@@ -40,7 +46,8 @@ class CudaBackend:
 
     # -- integer expected table of the shard: int64 [K] (S1) or [K, K] (S2), on the device
     def expected_table(self, cnt, width, saliency):
-        n1, n2 = engine.expected_tables(cnt, width, want_s1=saliency == 1, want_s2=saliency == 2)
+        with timing.stage("kernels", sync_cuda=True):
+            n1, n2 = engine.expected_tables(cnt, width, want_s1=saliency == 1, want_s2=saliency == 2)
         return n1 if saliency == 1 else n2
 
     def normalize(self, counts):
@@ -54,10 +61,11 @@ class CudaBackend:
         """`exact`: evaluate the S2 terms one by one with the reference's float64 expression (EPI_SCORE_DIRECT) instead
         of the tensor-core TABLE form; S1 is exact either way (its value table is built with that expression)."""
         exp = exp.to(self.device).contiguous()
-        if saliency == 1:
-            return engine.scores_s1(cnt, width, exp)
-        return engine.scores_s2(cnt, width, exp, perms=perms,
-                                mode=engine.EPI_SCORE_DIRECT if exact else engine.EPI_SCORE_TABLE)
+        with timing.stage("kernels", sync_cuda=True):
+            if saliency == 1:
+                return engine.scores_s1(cnt, width, exp)
+            return engine.scores_s2(cnt, width, exp, perms=perms,
+                                    mode=engine.EPI_SCORE_DIRECT if exact else engine.EPI_SCORE_TABLE)
 
     # -- S3 ------------------------------------------------------------------------------------------
     def states_to_device(self, states0):

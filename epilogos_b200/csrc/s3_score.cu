@@ -249,10 +249,7 @@ s3_score_kernel(const uint8_t* __restrict__ xt, long long bp, long long bins, in
             // The slab goes back to the producer only after its look-ups have returned.  SYM: the read-modify-write of the
             // score row above depends on every loaded term and precedes the arrive in program order.  Ordered-pair kernel:
             // the arrive takes the last loaded value as an operand (mbar_arrive_after, common.cuh).
-            if (lane == 0) {
-                if (SYM) mbar_arrive(&empty[s]);
-                else mbar_arrive_after(&empty[s], dep);
-            }
+            if (lane == 0) mbar_arrive_after(&empty[s], dep);
             if (++s == nslab) {
                 s = 0;
                 ph ^= 1;

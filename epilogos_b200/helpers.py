@@ -76,6 +76,12 @@ def read_matrix(path, rows=None, want_locations=True, num_states=127, pinned=Fal
     path = Path(path)
     if not path.is_file():
         raise FileNotFoundError(str(path))
+    from . import timing
+    with timing.stage("inflate+parse"):
+        return _read_matrix(path, rows, want_locations, num_states, pinned, shape, split, return_total)
+
+
+def _read_matrix(path, rows, want_locations, num_states, pinned, shape, split, return_total):
     if rows is not None and shape is not None:
         total, cols = shape
         lo, hi = int(rows[0]), int(rows[1])
@@ -185,13 +191,15 @@ def savez_level(path, level=1, **arrays):
     zlib's default 6 -- these score matrices are dominated by repeated quiescent rows and pack almost as well at a
     quarter of the time (whole chr1: temp_scores 0.38 s instead of 1.56 s, genome_stats 0.9 s instead of 3.2 s)."""
     import zipfile
+    from . import timing
     path = Path(path)
     if path.suffix != ".npz":
         path = path.with_name(path.name + ".npz")
-    with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=level) as zf:
-        for name, arr in arrays.items():
-            with zf.open(name + ".npy", "w", force_zip64=True) as f:
-                np.lib.format.write_array(f, np.asanyarray(arr), allow_pickle=True)
+    with timing.stage("npz hand-over files"):
+        with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=level) as zf:
+            for name, arr in arrays.items():
+                with zf.open(name + ".npy", "w", force_zip64=True) as f:
+                    np.lib.format.write_array(f, np.asanyarray(arr), allow_pickle=True)
 
 
 def sharedToNumpy(sharedArr, numRows, numStates):

@@ -50,7 +50,9 @@ def calculateScores(saliency, file1Path, numStates, outputDirPath, expFreqPath, 
     scoreArr = dist.gather_rows(local, shard.total_rows)
     loc = _gather_locations(shard)
     if dist.rank() == 0:
-        scoreArr = scoreArr.cpu().numpy()
+        from . import timing
+        with timing.stage("device -> host", sync_cuda=True):
+            scoreArr = scoreArr.cpu().numpy()
         writer.write_scores_text(outputDirPath / "scores_{}_{}.txt.gz".format(fileTag, filename), scoreArr, loc)
         chrName = loc["chrom"][0] if len(loc["chrom"]) else ""
         helpers.savez_level(outputDirPath / "temp_scores_{}_{}.npz".format(fileTag, filename),

@@ -23,9 +23,11 @@ def write_scores_text(path, scores32, loc, level=6, threads=0):
         names = names or b"\0"
     starts = np.ascontiguousarray(loc["start"], dtype=np.int64)
     ends = np.ascontiguousarray(loc["end"], dtype=np.int64)
-    _lib.call("epi_write_scores_gz", str(path).encode(), ctypes.c_char_p(names), ctypes.c_void_p(cid.ctypes.data),
-              ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
-              ctypes.c_void_p(scores32.ctypes.data), rows, k, int(level), int(threads))
+    from . import timing
+    with timing.stage("format %.5f + deflate"):
+        _lib.call("epi_write_scores_gz", str(path).encode(), ctypes.c_char_p(names), ctypes.c_void_p(cid.ctypes.data),
+                  ctypes.c_void_p(starts.ctypes.data), ctypes.c_void_p(ends.ctypes.data),
+                  ctypes.c_void_p(scores32.ctypes.data), rows, k, int(level), int(threads))
 
 
 def location_array(loc):

@@ -114,6 +114,50 @@ def real_full_case():
     print("wrote real10_chr1_full")
 
 
+def roi_wide_case():
+    """Region-of-interest rankings at the benchmark width (833 biosamples, 18 states) from the UNMODIFIED reference:
+    expected + scores for S1 and S2 on 24,000 synthetic bins (8 worker processes), S3 on the first 160 of them, then the
+    reference's own helpers.maxMean on scoreArr.sum(axis=1) (roiSingle.py:118-119) with windows of 50 bins.  The matrix is not
+    stored (it is regenerated from its seed, orc.synth_states(24000, 833, 18, seed=77)); a sha256 of it guards the
+    generator.  Also S2 of the 4000-bin real-data slice (10 biosamples)."""
+    import warnings
+    bins, cols, k, seed = 24000, 833, 18, 77
+    x = orc.synth_states(bins, cols, k, seed)
+    out = {"bins": np.int64(bins), "cols": np.int64(cols), "num_states": np.int64(k), "seed": np.int64(seed),
+           "x_sha256": np.frombuffer(hashlib.sha256(np.ascontiguousarray(x).tobytes()).digest(), np.uint8)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref._import_reference()
+        from epilogos.helpers import maxMean
+
+    def rank(scores, width, tag):
+        n = len(scores)
+        loc = np.empty((n, 3), dtype=object)
+        loc[:, 0] = "chr1"; loc[:, 1] = np.arange(n) * 200; loc[:, 2] = np.arange(n) * 200 + 200
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rois, idx = maxMean(np.concatenate((loc, scores.sum(axis=1).reshape(n, 1)), axis=1), width, 100)
+        out[tag + "_roi_original_idx"] = np.asarray(idx).astype(np.int64)
+        out[tag + "_roi_start"] = rois["Start"].to_numpy(np.int64)
+        out[tag + "_roi_end"] = rois["End"].to_numpy(np.int64)
+        out[tag + "_roi_rolling_max"] = rois["RollingMax"].to_numpy(np.float64)
+        out[tag + "_scores_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(scores).tobytes()).digest(), np.uint8)
+
+    for s in (1, 2):
+        r = ref.run_single(x, k, s, nproc=8)
+        out["s%d_exp" % s] = r["exp"]
+        rank(r["scores"], 50, "s%d" % s)
+    r3 = ref.run_single(x[:160], k, 3, nproc=2)
+    out["s3_scores"] = r3["scores"]
+    rank(r3["scores"], 5, "s3")
+    real = real_slice()
+    r = ref.run_single(real, 18, 2)
+    out["real_s2_exp"] = r["exp"]
+    rank(r["scores"], 50, "real_s2")
+    np.savez_compressed(HERE / "roi_wide_c833_k18.npz", **out)
+    print("wrote roi_wide_c833_k18", {k_: getattr(v, "shape", None) for k_, v in out.items()})
+
+
 def simsearch_case():
     """similaritySearch_calc.runEuclideanDistance of the reference on a synthetic reduced genome:
     continuous scores with a flat background on half of the bins (so that the mode of the distances exists, as it does
@@ -306,6 +350,8 @@ def main():
         s3_big_case("synth_s3_c833_k18")
     if want("roi"):
         roi_cases()
+    if want("roi_wide"):
+        roi_wide_case()
     if want("real_full"):
         real_full_case()
     if want("simsearch"):

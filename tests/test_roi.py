@@ -72,3 +72,30 @@ def test_roi_file_and_max_states(golden, tmp_path):
     roi.main(tmp_path, meta, "t", exp_path, 50, False)
     assert (tmp_path / "regionsOfInterest_t.txt").read_text() == want
     assert not exp_path.exists() and not list(tmp_path.glob("temp_scores_*.npz"))      # roiSingle.py:40, 73-74
+
+
+def wide_case(golden):
+    import hashlib
+    g = golden("roi_wide_c833_k18")
+    x = orc.synth_states(int(g["bins"]), int(g["cols"]), int(g["num_states"]), int(g["seed"]))
+    assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).digest() == g["x_sha256"].tobytes(), \
+        "the synthetic generator no longer reproduces the matrix the reference was run on"
+    return g, x
+
+
+@pytest.mark.parametrize("tag", ["s1", "s2"])
+def test_wide_833_rankings_match_reference(golden, tag):
+    """833 biosamples x 18 states, 24,000 bins: the oracle's float32 scores carry the reference's sha256, and both the
+    oracle's and the native selector's top-100 equal the reference's own helpers.maxMean ranking, region by region."""
+    import hashlib
+    from epilogos_b200 import roi
+    g, x = wide_case(golden)
+    k = int(g["num_states"])
+    scores = orc.s1_scores(x, k, g["s1_exp"]) if tag == "s1" else orc.s2_scores(x, k, g["s2_exp"])
+    assert hashlib.sha256(np.ascontiguousarray(scores).tobytes()).digest() == g[tag + "_scores_sha256"].tobytes()
+    starts = np.arange(len(x), dtype=np.int64) * 200
+    for sel in (roi_oracle.max_mean(starts, starts + 200, scores.sum(axis=1), 50, 100),
+                roi.max_mean(starts, starts + 200, scores.sum(axis=1), 50, 100)):
+        assert np.array_equal(sel["original_idx"], g[tag + "_roi_original_idx"])
+        assert np.array_equal(sel["start"], g[tag + "_roi_start"]) and np.array_equal(sel["end"], g[tag + "_roi_end"])
+        assert sel["rolling_max"].tobytes() == g[tag + "_roi_rolling_max"].tobytes()
