@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- bins/sec for expected + scores on B200 (BASELINE.json metric), plus the CPU reference arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--saliency 2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config ...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one synthetic matrix that is already resident in HBM:
 K1 counts -> K2 expected table (tensor-core Gram of the count bytes) -> (allreduce over ranks) -> K4 normalise ->
 K5 scores (S2: table preparation + tensor-core mat-vec kernel + the gated DIRECT fallback = 6 launches per step).
-Workload at every N: BASELINE.json configs[1], S2 on 15.5 M bins x 833 biosamples x 18 states PER GPU
+Workload of `value` at every N: BASELINE.json configs[1], S2 on 15.5 M bins x 833 biosamples x 18 states PER GPU
 (weak scaling; the bins shard with no data-path collective, only the 18x18 table is all-reduced).
 The matrix (13 GB) is far larger than L2 (126 MB), so no L2 flush is needed between steps.
 
-`e2e` is the same metric through epi_single_host (the reference-facing C-ABI call) with the matrix in
-pinned HOST memory: H2D of the matrix and D2H of tables + scores are inside the timed region.
+Beside it, in the same JSON line:
+  check         the all-reduced integer table equals its closed form on every rank (correctness travels with the number)
+  target        the north-star configuration: ONE genome sharded over the N GPUs (strong scaling) for S2 and S1, eager and
+                as a captured CUDA graph, and ONE chr1 for S3 with Gram / tile all-reduce / scores timed separately
+  e2e           the same metric through the reference-facing C-ABI calls with pinned HOST buffers, H2D and D2H inside the
+                timed region (epi_single_host_packed: the matrix in the 4/5-bit packed transport layout; the int8 variant
+                beside it; S3 and paired configurations through epi_s3_host / epi_paired_host)
+  cpu_baseline  N = 1 only: the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) on the box's host cores
 
-`--impl reference` times the CPU restatement of the reference's row-loop algorithm (oracle/, kind "port":
-the reference is pure Python and cannot travel to the GPU box) with all host cores on a bounded sample.
+`--impl reference` times that reference -- expected.main -> expectedCombination.main -> scores.main with one worker
+process per core on a bounded TSV.gz sample of the workload, parse and gz write included (kind "reference"; the oracle's
+row-loop port is the fallback when nothing was staged).
 """
 import argparse
 import json
