@@ -257,7 +257,7 @@ def run_reference(args):
     steps, warmup = max(1, args.steps), args.warmup
     if saliency == 3:               # one pass costs tens of seconds of fixed set-up per worker (693k-tuple pair list, 0.9 GB tables)
         steps, warmup = min(steps, 2), 0
-    base, times, n = cpu_arm(args, steps, warmup, budget_s=150.0)
+    base, times, n = cpu_arm(args, steps, warmup, budget_s=float(os.environ.get("EPI_BENCH_REF_BUDGET_S", "150")))
     sec = sum(times) / len(times)
     metric = ("bins/sec for paired expected+scores (S1)" if paired else "bins/sec for expected+scores (S%d)" % saliency)
     line = {

@@ -68,6 +68,8 @@ struct Reader {
 // "%.5f" of a double with printf semantics (round-half-even on the exact binary value).  Fast path: scale by 1e5 and
 // round; whenever the scaled value is within 1e-6 of a rounding boundary (or huge / non-finite) defer to snprintf.
 static inline char* format_5f(char* p, double d) {
+    if (d != d) return p + sprintf(p, "nan");                    // Python's "{:.5f}" prints nan without a sign; glibc "-nan"
+    if (isinf(d)) return p + sprintf(p, d < 0 ? "-inf" : "inf");
     if (!(fabs(d) < 1e9)) return p + sprintf(p, "%.5f", d);
     const bool neg = signbit(d);
     const double a = fabs(d) * 1e5;
@@ -189,6 +191,7 @@ struct LineSource {
     }
 
     // fill block w with the native decoder; returns the bytes produced (BLOCK unless the stream ended) or -1 on error
+    bool after_member_ = false;      // the previous decode call ended exactly at the end of a gzip member
     long long fill_native(int w, uint32_t& crc, uint64_t& member_bytes) {
         uint8_t* base = reinterpret_cast<uint8_t*>(text(w));
         uint8_t* out = base;
@@ -199,9 +202,20 @@ struct LineSource {
             const FastInflate::Status st = inflater.decode(out, end, &np);
             crc = (uint32_t)crc32(crc, out, (uInt)(np - out));
             member_bytes += (uint64_t)(np - out);
+            const bool produced = np != out;
             out = np;
-            if (st == FastInflate::ERROR) return -1;
+            if (st == FastInflate::ERROR) {
+                if (after_member_ && !produced) {
+                    // bytes after a complete member that are neither zero padding nor another gzip member: Python's gzip
+                    // module (the reference's reader) raises on them; zlib's gzread would silently ignore them
+                    error_ = path_ + ": trailing garbage after the last gzip member";
+                    return -2;
+                }
+                return -1;
+            }
+            after_member_ = false;
             if (st == FastInflate::MEMBER_END) {
+                after_member_ = true;
                 if (crc != inflater.member_crc() || (uint32_t)member_bytes != inflater.member_isize()) {
                     error_ = path_ + ": gzip member fails its CRC-32 / length check";
                     return -2;

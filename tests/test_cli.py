@@ -93,3 +93,33 @@ def test_cli_main_end_to_end_on_cpu_with_the_oracle_backend(tmp_path, golden, mo
     assert (out / "regionsOfInterest_mydata_s2.txt").exists()
     assert not list(out.glob("temp_*")) and not (out / "exp_freq_mydata_s2.npy").exists()
     session.clear()
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference`: rank 0 prints ONE JSON line with the contract's keys (the unmodified reference staged under
+    oracle/_ref when /root/reference exists, else the oracle port), the same `config` object our arm prints, e2e = value;
+    every other rank exits 0 without output."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, EPI_BENCH_REF_BUDGET_S="3")
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--config", "s2_genome_127"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "bins/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["e2e"] == {"value": d["value"], "unit": "bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["biosamples"] == 127 and d["config"]["states"] == 15 and "workload" in d["config"]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""

@@ -283,3 +283,34 @@ def test_host_packer_layout(cols, k):
     assert bits == (4 if k <= 16 else 5)
     assert packed.shape == (bins, engine.packed_pitch(cols, bits))
     assert np.array_equal(packed.numpy(), _pack_reference(x, cols, bits))
+
+
+def test_writer_non_finite_values_print_like_python(tmp_path):
+    """scores.writeScores formats with Python's "{:.5f}": nan (never "-nan"), inf, -inf."""
+    vals = np.array([[np.nan, -np.nan, np.inf, -np.inf, 1.5]], dtype=np.float32)
+    vals.view(np.uint32)[0, 1] |= 0x80000000                        # a NaN with the sign bit set
+    loc = dict(chrom=np.array(["chr1"], dtype=object), start=np.zeros(1, np.int64), end=np.full(1, 200, np.int64))
+    path = tmp_path / "nf.txt.gz"
+    writer.write_scores_text(path, vals, loc)
+    got = gzip.open(path, "rb").read().decode()
+    assert got == "chr1\t0\t200\t" + "\t".join("{:.5f}".format(float(v)) for v in vals[0]) + "\n"
+    assert got.split("\t")[3:5] == ["nan", "nan"]
+
+
+def test_trailing_garbage_after_gzip_members_is_an_error(tmp_path):
+    """Python's gzip module (the reference's reader) raises on bytes after the last member that are not another member; zero
+    padding is tolerated.  zlib's gzread would silently accept both."""
+    rows = "".join("chr1\t%d\t%d\t1\t2\t3\n" % (i * 200, i * 200 + 200) for i in range(50))
+    good = gzip.compress(rows.encode())
+    ok = tmp_path / "ok.txt.gz"
+    ok.write_bytes(good + b"\0" * 64)
+    assert helpers.read_matrix(ok, num_states=3)[1].shape == (50, 3)
+    two = tmp_path / "two.txt.gz"
+    two.write_bytes(good + good)
+    assert helpers.read_matrix(two, num_states=3)[1].shape == (100, 3)
+    bad = tmp_path / "bad.txt.gz"
+    bad.write_bytes(good + b"this is not gzip data, 1234567890 1234567890")
+    with pytest.raises(EpilogosB200Error):
+        helpers.read_matrix(bad, num_states=3)
+    with pytest.raises(Exception):
+        gzip.open(bad, "rb").read()                                  # the reference's reader refuses it as well
