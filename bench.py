@@ -18,7 +18,7 @@ Beside it, in the same JSON line:
   e2e           the same metric through the reference-facing C-ABI calls with pinned HOST buffers, H2D and D2H inside the
                 timed region (epi_single_host_packed: the matrix in the 4/5-bit packed transport layout; the int8 variant
                 beside it; S3 and paired configurations through epi_s3_host / epi_paired_host)
-  cpu_baseline  N = 1 only: the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) on the box's host cores
+  cpu_baseline  N = 1 only: the UNMODIFIED reference (oracle/_ref, byte-compiled by __graft_entry__.build()) on the box's host cores
 
 `--impl reference` times that reference -- expected.main -> expectedCombination.main -> scores.main with one worker
 process per core on a bounded TSV.gz sample of the workload, parse and gz write included (kind "reference"; the oracle's
@@ -70,7 +70,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm.  kind "reference": the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_reference.py from
+# CPU arm.  kind "reference": the UNMODIFIED reference (oracle/_ref, byte-compiled by oracle/stage_reference.py from
 # /root/reference) runs its own expected.main -> expectedCombination.main -> scores.main on a TSV.gz sample of the
 # workload with one worker process per host core -- what `epilogos -l -c 0` executes before the ROI step (run.py:191-279),
 # TSV parse and gz write included; its own verbose timers give the compute-only share.  kind "port": the oracle's
@@ -243,7 +243,7 @@ def cpu_arm(args, steps, warmup, budget_s):
         return reference_cpu_arm(args, steps, warmup, budget_s)
     _, cols, k, _ = CONFIGS[args.config]
     if args.config.startswith("paired") or args.config[1] == "3":
-        raise RuntimeError("the reference is not staged under oracle/_ref and the port covers S1/S2 only")
+        raise RuntimeError("the reference was not built into oracle/_ref and the port covers S1/S2 only")
     return port_cpu_arm(cols, k, int(args.config[1]), steps, warmup, budget_s)
 
 

@@ -1,19 +1,23 @@
-"""Stage the UNMODIFIED reference package next to the oracle so that it can travel to the GPU box.
+"""Build the UNMODIFIED reference into a form that can travel to the GPU box.
 
-TEST / BENCHMARK INFRASTRUCTURE ONLY.  The reference (meuleman/epilogos) is pure Python, so there is nothing to
-compile: "building" oracle/_ref means copying the package's own source files, byte for byte, from where they lie under
-/root/reference into oracle/_ref/epilogos/.  oracle/_ref/ is git-ignored (the sources never enter this repository's
-history) but NOT gpurun-ignored, so the staged copy travels with the snapshot like a built .so and `bench.py --impl
-reference` / `cpu_baseline` can time the reference's real `expected.main -> expectedCombination.main -> scores.main`
-path (TSV.gz parse and gz write included, run.py:191-303) on the GPU box's own host cores.
+TEST / BENCHMARK INFRASTRUCTURE ONLY.  The reference (meuleman/epilogos) is pure Python, so "building" it means compiling:
+the modules the scoring path imports are byte-compiled with py_compile straight from where they lie under /root/reference
+into oracle/_ref/epilogos/*.pyc (sourceless layout, importable as the package `epilogos`).  No reference SOURCE is copied
+anywhere; oracle/_ref/ holds build outputs only, is git-ignored (nothing enters this repository's history) but NOT
+gpurun-ignored, so it travels with the snapshot like a built .so and `bench.py --impl reference` / `cpu_baseline` can time
+the reference's real `expected.main -> expectedCombination.main -> scores.main` path (TSV.gz parse and gz write included,
+run.py:191-303) on the GPU box's own host cores.  The GPU box runs the same image (same CPython), so the bytecode loads.
 
     python -m oracle.stage_reference          # called by __graft_entry__.build() when /root/reference exists
 
-A MANIFEST with the sha256 of every staged file is written so that a run can state exactly what it timed.
+A MANIFEST with the sha256 of every SOURCE file that was compiled is written so that a run can state exactly what it timed.
 """
 import hashlib
 import json
+import os
+import py_compile
 import shutil
+import sys
 from pathlib import Path
 
 SOURCE = Path("/root/reference")
@@ -26,44 +30,39 @@ FILES = ["epilogos/__init__.py", "epilogos/expected.py", "epilogos/expectedCombi
 
 def staged_root():
     """Directory to put on sys.path to import the reference: /root/reference when it exists (authoring container),
-    else the staged copy, else None."""
+    else the byte-compiled build under oracle/_ref, else None.  EPI_REF_FORCE_STAGED=1 prefers the build (tests)."""
+    built = (DEST / "epilogos" / "scores.pyc").is_file()
+    if built and os.environ.get("EPI_REF_FORCE_STAGED"):
+        return DEST
     if (SOURCE / "epilogos" / "scores.py").is_file():
         return SOURCE
-    if (DEST / "epilogos" / "scores.py").is_file():
-        return DEST
-    return None
+    return DEST if built else None
 
 
 def stage(verbose=True):
     if not (SOURCE / "epilogos" / "scores.py").is_file():
         if verbose:
-            print("stage_reference: %s not present, nothing staged" % SOURCE)
+            print("stage_reference: %s not present, nothing built" % SOURCE)
         return None
+    if (DEST / "epilogos").exists():
+        shutil.rmtree(DEST / "epilogos")
+    (DEST / "epilogos").mkdir(parents=True)
     manifest = {}
     for rel in FILES:
         src = SOURCE / rel
+        dst = DEST / (rel + "c")                      # epilogos/scores.pyc: sourceless import layout
         if not src.is_file():
-            if rel.endswith("__init__.py"):
-                (DEST / rel).parent.mkdir(parents=True, exist_ok=True)
-                (DEST / rel).write_bytes(b"")
-                manifest[rel] = hashlib.sha256(b"").hexdigest()
-                continue
             raise FileNotFoundError(src)
-        dst = DEST / rel
-        dst.parent.mkdir(parents=True, exist_ok=True)
-        shutil.copyfile(src, dst)
-        manifest[rel] = hashlib.sha256(dst.read_bytes()).hexdigest()
-    version = ""
-    setup = SOURCE / "setup.py"
-    if setup.is_file():
-        for line in setup.read_text().splitlines():
-            if "version" in line and "=" in line:
-                version = line.strip().strip(",")
-                break
-    (DEST / "MANIFEST.json").write_text(json.dumps({"source": str(SOURCE), "version_line": version, "sha256": manifest},
-                                                   indent=1))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")           # SyntaxWarnings of the reference's own regex literals
+            py_compile.compile(str(src), cfile=str(dst), dfile="<reference>/" + rel, doraise=True, optimize=0, quiet=1)
+        manifest[rel] = hashlib.sha256(src.read_bytes()).hexdigest()
+    (DEST / "MANIFEST.json").write_text(json.dumps({"source": str(SOURCE), "python": sys.version.split()[0],
+                                                   "what": "py_compile of the listed reference sources (sha256 of each source)",
+                                                   "sha256": manifest}, indent=1))
     if verbose:
-        print("stage_reference: %d files -> %s" % (len(manifest), DEST))
+        print("stage_reference: %d modules byte-compiled -> %s" % (len(manifest), DEST))
     return DEST
 
 
