@@ -414,3 +414,35 @@ def test_shuffled_widths_follow_numpy_slicing():
         sh = np.zeros((1, c1 + c2))
         want = (c1, c2) if g == -1 else (sh[:, :g].shape[1], sh[:, g:2 * g].shape[1])
         assert shuffled_widths(c1, c2, g) == want
+
+
+@pytest.mark.parametrize("shard", ["rows", "files"])
+def test_run_stages_world_size_eight(tmp_path, shard):
+    """The 8-GPU shape of the CLI on gloo: eight ranks, eight input files of different sizes (some shorter than the world
+    size times a few rows), rows split over the ranks or whole files dealt to them -- every score file equals the
+    single-process oracle result for the table of ALL files, and step 4 runs once."""
+    from oracle import epilogos_oracle as orc
+    from test_cli import META
+    parts = {"epilogos_matrix_chr%d" % (i + 1): orc.synth_states(90 + 37 * i, 40, 18, seed=i) for i in range(8)}
+    inp = tmp_path / "in"; out = tmp_path / "out"
+    inp.mkdir(); out.mkdir()
+    for name, part in parts.items():
+        write_tsv(inp / (name + ".txt"), part, chrom=name.split("_")[-1])
+    meta = tmp_path / "meta.tsv"
+    meta.write_text(META)
+    port = 35500 + (os.getpid() % 2000) + (11 if shard == "files" else 0)
+    code = FILES_WORKER.format(root=str(ROOT), tests=str(ROOT / "tests"), port=port, out=str(out), inp=str(inp),
+                               meta=str(meta), shard=shard).replace("world_size=2", "world_size=8")
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(8)]
+    logs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    allx = np.concatenate(list(parts.values()))
+    exp = orc.normalize_expected(orc.s2_expected_counts(allx, 18))
+    for name, part in parts.items():
+        ref = orc.s2_scores(part, 18, exp)
+        with gzip.open(out / ("scores_in_s2_%s.txt.gz" % name), "rb") as gzf:
+            text = gzf.read()
+        starts = np.arange(part.shape[0]) * 200
+        assert text == orc.format_scores_text(ref, name.split("_")[-1], starts, starts + 200)
+    assert (out / "regionsOfInterest_in_s2.txt").exists() and not list(out.glob("temp_*"))
