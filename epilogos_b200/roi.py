@@ -48,17 +48,26 @@ def max_mean(starts, ends, score, window, max_regions=100):
 
 def readInData(outputDirPath):
     """All temp_scores_*.npz in chromosome order -> (chrom per row, starts, ends, scoreArr); temp files removed."""
-    files = list(Path(outputDirPath).glob("temp_scores_*.npz"))
+    from . import session
+    outputDirPath = Path(outputDirPath)
+    files = list(outputDirPath.glob("temp_scores_*.npz"))
     chunks = {}
     for f in files:
         z = np.load(f, allow_pickle=True)
-        chunks[str(z["chrName"][0])] = (z["scoreArr"], z["locationArr"])
+        loc = z["locationArr"]
+        chunks[str(z["chrName"][0])] = (z["scoreArr"], loc[:, 0], loc[:, 1].astype(np.int64), loc[:, 2].astype(np.int64))
+    # files of this directory that the score stage of this process handed over in memory instead of writing them
+    for key in [k for k in session.handover if Path(k).parent == outputDirPath and Path(k).name.startswith("temp_scores_")]:
+        h = session.handover.pop(key)
+        chunks[h["chrName"]] = (h["scoreArr"], h["chrom"], h["start"], h["end"])
     order = orderChromosomes(list(chunks))
     scoreArr = np.concatenate([chunks[c][0] for c in order])
-    loc = np.concatenate([chunks[c][1] for c in order])
+    chrom = np.concatenate([np.asarray(chunks[c][1], dtype=object) for c in order])
+    starts = np.concatenate([chunks[c][2] for c in order])
+    ends = np.concatenate([chunks[c][3] for c in order])
     for f in files:
         remove(f)
-    return loc[:, 0], loc[:, 1].astype(np.int64), loc[:, 2].astype(np.int64), scoreArr
+    return chrom, starts, ends, scoreArr
 
 
 def createTopScoresTxt(filePath, chrom, starts, ends, scoreArr, nameArr, roiWidth):

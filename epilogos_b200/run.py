@@ -140,10 +140,21 @@ def run_stages(pairs, mode, numStates, saliency, outputDirPath, fileTag, storedE
     say("\nSTEP 2: Background frequency combination")
     expectedCombination.main(outputDirPath, storedExpPath, fileTag, verbose, backend=backend)
     say("\nSTEP 3: Score calculation")
-    with alone():
-        for f, f2 in mine:
-            scores.main(f, f2, numStates, saliency, outputDirPath, storedExpPath, fileTag, numProcesses, quiescentState,
-                        groupSize, verbose, backend=backend)
+    # step 4 runs in this process right after: rank 0 hands its score arrays over in memory instead of through
+    # temp_scores_*.npz (files written by other ranks, when whole files are dealt, are still read from disk)
+    try:
+        from . import roi as _roi_stage          # noqa: F401
+        roi_here = mode == "single" and dist.group_rank() == 0
+    except ImportError:
+        roi_here = False
+    session.handover_enabled = roi_here
+    try:
+        with alone():
+            for f, f2 in mine:
+                scores.main(f, f2, numStates, saliency, outputDirPath, storedExpPath, fileTag, numProcesses, quiescentState,
+                            groupSize, verbose, backend=backend)
+    finally:
+        session.handover_enabled = False
     dist.barrier()
     if mode == "single":
         say("\nSTEP 4: Finding regions of interest")

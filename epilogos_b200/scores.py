@@ -55,8 +55,15 @@ def calculateScores(saliency, file1Path, numStates, outputDirPath, expFreqPath, 
             scoreArr = scoreArr.cpu().numpy()
         writer.write_scores_text(outputDirPath / "scores_{}_{}.txt.gz".format(fileTag, filename), scoreArr, loc)
         chrName = loc["chrom"][0] if len(loc["chrom"]) else ""
-        helpers.savez_level(outputDirPath / "temp_scores_{}_{}.npz".format(fileTag, filename),
-                            chrName=np.array([chrName]), scoreArr=scoreArr, locationArr=writer.location_array(loc))
+        npz = outputDirPath / "temp_scores_{}_{}.npz".format(fileTag, filename)
+        import os
+        if session.handover_enabled and not os.environ.get("EPILOGOS_B200_KEEP_TEMP"):
+            # the ROI stage runs next, in this process: hand the arrays over in memory (session.handover)
+            session.handover[str(npz)] = dict(chrName=str(chrName), scoreArr=scoreArr, chrom=loc["chrom"],
+                                              start=np.asarray(loc["start"], dtype=np.int64),
+                                              end=np.asarray(loc["end"], dtype=np.int64))
+        else:
+            helpers.savez_level(npz, chrName=np.array([chrName]), scoreArr=scoreArr, locationArr=writer.location_array(loc))
 
 
 def _gather_locations(shard):

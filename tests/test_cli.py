@@ -93,6 +93,24 @@ def test_cli_main_end_to_end_on_cpu_with_the_oracle_backend(tmp_path, golden, mo
     assert (out / "regionsOfInterest_mydata_s2.txt").exists()
     assert not list(out.glob("temp_*")) and not (out / "exp_freq_mydata_s2.npy").exists()
     session.clear()
+    # the score -> ROI hand-over happened in memory (no temp_scores npz was ever written) and gives the very file that
+    # the reference's route through temp_scores_*.npz gives (EPILOGOS_B200_KEEP_TEMP=1)
+    assert not session.handover
+    from epilogos_b200 import helpers
+    written = []
+    real = helpers.savez_level
+    monkeypatch.setattr(helpers, "savez_level", lambda path, *a, **k: (written.append(str(path)), real(path, *a, **k))[1])
+    out1 = tmp_path / "out_mem"
+    r = CliRunner().invoke(run.main, ["-l", "-i", str(inp), "-o", str(out1), "-j", str(meta), "-s", "2", "-w", "20"])
+    assert r.exit_code == 0 and not [w for w in written if "temp_scores" in w]
+    monkeypatch.setenv("EPILOGOS_B200_KEEP_TEMP", "1")
+    session.clear()
+    out2 = tmp_path / "out_files"
+    r = CliRunner().invoke(run.main, ["-l", "-i", str(inp), "-o", str(out2), "-j", str(meta), "-s", "2", "-w", "20"])
+    assert r.exit_code == 0 and len([w for w in written if "temp_scores" in w]) == 2
+    assert (out1 / "regionsOfInterest_mydata_s2.txt").read_text() == (out2 / "regionsOfInterest_mydata_s2.txt").read_text()
+    assert (out / "regionsOfInterest_mydata_s2.txt").read_text() == (out2 / "regionsOfInterest_mydata_s2.txt").read_text()
+    session.clear()
 
 
 def test_bench_reference_arm_contract(tmp_path):
