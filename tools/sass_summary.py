@@ -4,7 +4,6 @@ bulk copies (UBLKCP), mbarrier phase checks (SYNCS), plus the register count of 
     python tools/sass_summary.py > profiles/r02_sass_summary.txt          (runs without a GPU)"""
 import re
 import subprocess
-import sys
 from collections import Counter, OrderedDict
 from pathlib import Path
 
