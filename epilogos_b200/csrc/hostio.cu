@@ -23,6 +23,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -382,6 +383,37 @@ struct LineSource {
         }
     }
     std::vector<char> line_buf;
+
+    // Every complete line that can be handed out without letting go of the current block (the first one may be the line
+    // that straddled the previous block boundary; it lives in line_buf).  The pointers stay valid until the next call.
+    // Returns false at end of file; an unterminated tail at the end of the file is not a line (countRows semantics) and
+    // is dropped.  Do not mix with next_line().
+    bool next_batch(std::vector<std::pair<const char*, const char*>>& lines) {
+        lines.clear();
+        for (;;) {
+            const char* base = text(cur);
+            const size_t len = lens[cur];
+            while (pos < len) {
+                const char* nl = static_cast<const char*>(memchr(base + pos, '\n', len - pos));
+                if (nl == nullptr) break;
+                if (!carry.empty()) {
+                    carry.insert(carry.end(), base + pos, nl);
+                    line_buf.swap(carry);
+                    carry.clear();
+                    lines.emplace_back(line_buf.data(), line_buf.data() + line_buf.size());
+                } else {
+                    lines.emplace_back(base + pos, nl);
+                }
+                pos = (size_t)(nl - base) + 1;
+            }
+            if (!lines.empty()) return true;           // the partial tail is picked up by the next call
+            if (pos < len) {
+                carry.insert(carry.end(), base + pos, base + len);
+                pos = len;
+            }
+            if (!next_block()) return false;
+        }
+    }
     ~LineSource() {
         if (worker.joinable()) {
             {
@@ -557,34 +589,97 @@ struct ParsedFile {
 };
 }  // namespace epi
 
+// Number of parser threads for one file: the inflate thread of every file being read plus its parsers should fit the
+// machine, so a single file gets up to four parsers and a directory read file-parallel (session.prefetch) one per file.
+static std::atomic<int> g_active_parses{0};
+static int parse_threads() {
+    if (const char* e = getenv("EPI_PARSE_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1) return v > 16 ? 16 : v;
+    }
+    const int cores = (int)std::thread::hardware_concurrency();
+    const int active = std::max(1, g_active_parses.load());
+    return std::max(1, std::min(4, cores / active - 1));
+}
+
 extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out,
                                   int32_t* cols_out, int32_t* n_chrom_out, int32_t* names_bytes_out) {
     EPI_REQUIRE(path != nullptr && handle_out != nullptr, "null pointer argument");
     EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
     LineSource src;
     EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    struct ActiveGuard {
+        ActiveGuard() { ++g_active_parses; }
+        ~ActiveGuard() { --g_active_parses; }
+    } guard;
     std::unique_ptr<ParsedFile> pf(new ParsedFile());
-    const char *p, *e;
-    bool has_nl;
+    std::vector<std::pair<const char*, const char*>> lines;
     int last_id = -1;
-    while (src.next_line(p, e, has_nl)) {
-        if (!has_nl) break;                           // rows = newline count (helpers.countRows): an unterminated tail is not a row
-        if (pf->rows == 0) {
+    // The inflate thread hands over 16 MB blocks; all complete lines of a block are split here (memchr), the chromosome
+    // names resolved (serial: the name table grows), and the rows -- whose indices, hence destinations, are known by now --
+    // parsed by a few threads.  Parsing (4 ns per label) was the slower of the two pipelined stages; with it spread out
+    // the single-stream inflate bounds the read.
+    while (src.next_batch(lines)) {
+        const int64_t n = (int64_t)lines.size(), r0 = pf->rows;
+        if (r0 == 0) {
             int tabs = 0;
-            for (const char* q = p; q < e; ++q) tabs += (*q == '\t');
+            for (const char* q = lines[0].first; q < lines[0].second; ++q) tabs += (*q == '\t');
             pf->cols = tabs + 1 - 3;
             EPI_REQUIRE(pf->cols >= 1, "%s: expected `chr start end state_1 ...` rows", path);
         }
-        const int64_t r = pf->rows;
-        if (r % ParsedFile::CHUNK_ROWS == 0) pf->labels.emplace_back((size_t)ParsedFile::CHUNK_ROWS * pf->cols);
-        int8_t* dst = pf->labels.back().data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
-        int64_t st = 0, en = 0;
-        int32_t cid = 0;
-        if (int rc = parse_row(path, r, p, e, pf->cols, num_states, dst, &st, &en, &cid, pf->names, last_id, true)) return rc;
-        pf->starts.push_back(st);
-        pf->ends.push_back(en);
-        pf->chrom.push_back(cid);
-        ++pf->rows;
+        while ((int64_t)pf->labels.size() * ParsedFile::CHUNK_ROWS < r0 + n)
+            pf->labels.emplace_back((size_t)ParsedFile::CHUNK_ROWS * pf->cols);
+        pf->starts.resize((size_t)(r0 + n));
+        pf->ends.resize((size_t)(r0 + n));
+        pf->chrom.resize((size_t)(r0 + n));
+        for (int64_t i = 0; i < n; ++i) {             // chromosome ids (the row's other fields are validated by parse_row)
+            const char* p = lines[(size_t)i].first;
+            const char* e = lines[(size_t)i].second;
+            const char* t = static_cast<const char*>(memchr(p, '\t', (size_t)(e - p)));
+            const size_t nl = t ? (size_t)(t - p) : (size_t)(e - p);
+            int id = -1;
+            if (last_id >= 0 && pf->names[(size_t)last_id].size() == nl && memcmp(pf->names[(size_t)last_id].data(), p, nl) == 0)
+                id = last_id;
+            for (size_t q = 0; id < 0 && q < pf->names.size(); ++q)
+                if (pf->names[q].size() == nl && memcmp(pf->names[q].data(), p, nl) == 0) id = (int)q;
+            if (id < 0) {
+                if (t == nullptr) break;               // a truncated row: parse_row reports it
+                id = (int)pf->names.size();
+                pf->names.emplace_back(p, nl);
+            }
+            pf->chrom[(size_t)(r0 + i)] = last_id = id;
+        }
+        const int nt = (int)std::min<int64_t>(parse_threads(), std::max<int64_t>(1, n / 256));
+        std::vector<std::string> errs((size_t)nt);
+        std::vector<int64_t> err_row((size_t)nt, -1);
+        auto work = [&](int t) {
+            std::vector<std::string> no_names;
+            int no_last = -1;
+            int32_t cid = 0;
+            for (int64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+                const int64_t r = r0 + i;
+                int8_t* dst = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+                if (parse_row(path, r, lines[(size_t)i].first, lines[(size_t)i].second, pf->cols, num_states, dst,
+                              &pf->starts[(size_t)r], &pf->ends[(size_t)r], &cid, no_names, no_last, false)) {
+                    errs[(size_t)t] = epi_last_error();        // the message lives in this thread's error slot
+                    err_row[(size_t)t] = r;
+                    return;
+                }
+            }
+        };
+        if (nt == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nt; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        for (int t = 0; t < nt; ++t)                  // threads own ascending row ranges: the first failure is the lowest row
+            if (err_row[(size_t)t] >= 0) {
+                set_error("%s", errs[(size_t)t].c_str());
+                return 2;
+            }
+        pf->rows = r0 + n;
     }
     EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     size_t nb = 0;
