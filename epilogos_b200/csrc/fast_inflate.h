@@ -17,7 +17,10 @@
 
 namespace epi {
 
+class MarkerDecoder;
+
 class FastInflate {
+    friend class MarkerDecoder;          // parallel_inflate.h shares the table builder and the entry encoding
 public:
     enum Status { OUT_FULL = 0, MEMBER_END = 1, ERROR = 2 };
 
@@ -418,6 +421,11 @@ private:
                 produced_ += (uint64_t)(out - start);
                 *out_pos = out;
                 return 0;
+            }
+            if (overrun()) {             // a stream cut short: the zero padding may decode as literals for ever
+                err_ = "truncated deflate stream";
+                *out_pos = out;
+                return 2;
             }
             refill();
             uint32_t e = lit_[bitbuf_ & lmask];

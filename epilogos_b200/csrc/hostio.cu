@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <memory>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -28,8 +29,33 @@
 
 #include "common.cuh"
 #include "fast_inflate.h"
+#include "parallel_inflate.h"
 
 namespace epi {
+
+// Thread budget of one reader.  Every file being read has an inflate stage and a parse stage; several files may be read
+// at once (session.prefetch) and, under torchrun, several ranks share the host (LOCAL_WORLD_SIZE), so the machine's
+// cores are divided by both before a reader takes its share.
+static std::atomic<int> g_active_readers{0};
+static int cores_per_reader() {
+    int cores = (int)std::thread::hardware_concurrency();
+    if (cores < 1) cores = 1;
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    const int active = std::max(1, g_active_readers.load());
+    return std::max(1, cores / (ranks * active));
+}
+// what the calling thread's last reader did (epi_reader_stats): mode, chunks, chunks with a start, chunks accepted
+static thread_local int64_t t_reader_stats[4] = {0, 0, 0, 0};
+// threads that decode ONE gzip stream in parallel (parallel_inflate.h); 1 = the sequential decoder
+static int inflate_threads() {
+    if (const char* e = getenv("EPI_INFLATE_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1) return v > 32 ? 32 : v;
+    }
+    const int t = std::min(8, cores_per_reader() / 2);
+    return t < 2 ? 1 : t;
+}
 
 struct Reader {
     gzFile gz = nullptr;       // gzopen reads plain files transparently as well
@@ -166,7 +192,10 @@ struct LineSource {
     std::string error_;                 // set by the worker before its last block is published
     std::vector<uint8_t> packed;        // the whole compressed file (native decoder)
     FastInflate inflater;
+    ParallelInflate pinflater;          // several threads on the one stream (large files, when cores are free)
     bool native = false;
+    bool parallel = false;
+    bool counted_ = false;
     uint64_t delivered = 0;             // bytes handed to the parser in complete blocks
 
     char* text(int w) { return blocks[w].data() + HIST; }
@@ -229,8 +258,24 @@ struct LineSource {
         return (long long)(out - base);
     }
 
+    // next piece of text from the parallel decoder into block w: bytes, 0 at the end of the stream, -1 = it gave up
+    // (the caller falls back to zlib from the bytes already delivered), -2 = error_ is set
+    long long fill_parallel(int w) {
+        size_t n = 0;
+        const int r = pinflater.next(blocks[w], &n);      // swaps the text buffer in; the old one is recycled
+        if (r == 1) return (long long)n;
+        if (r == 0) return 0;
+        if (r == -2) {
+            error_ = path_ + ": trailing garbage after the last gzip member";
+            return -2;
+        }
+        return -1;
+    }
+
     bool open(const char* path) {
         path_ = path;
+        ++g_active_readers;
+        counted_ = true;
         native = load_packed(path);
         if (!native) {
             gz = gzopen(path, "rb");
@@ -238,6 +283,18 @@ struct LineSource {
             gzbuffer(gz, 1 << 20);
         } else {
             inflater.reset(packed.data(), packed.size() - 16);
+            // large single files: decode the one stream with several threads
+            const size_t size = packed.size() - 16;
+            const int threads = inflate_threads();
+            size_t chunk = std::min<size_t>(1u << 20, std::max<size_t>(256u << 10, size / (size_t)(8 * std::max(1, threads))));
+            size_t least = 2u << 20;
+            if (const char* e = getenv("EPI_INFLATE_CHUNK")) {          // test / tuning knob: chunk bytes, no size threshold
+                if (atoll(e) > 0) {
+                    chunk = (size_t)atoll(e);
+                    least = 0;
+                }
+            }
+            if (threads >= 2 && size >= least) parallel = pinflater.start(packed.data(), size, threads, chunk, HIST);
         }
         blocks[0].resize(HIST + BLOCK + 64);
         blocks[1].resize(HIST + BLOCK + 64);
@@ -252,15 +309,31 @@ struct LineSource {
                     if (abort_) return;
                 }
                 long long n;
+                if (!parallel && blocks[w].size() < HIST + BLOCK + 64) blocks[w].resize(HIST + BLOCK + 64);   // after a parallel piece
                 if (native) {
-                    // the last 32 KiB of the previous block are the window of the next one
-                    if (delivered) memcpy(blocks[w].data(), text(w ^ 1) + BLOCK - HIST, HIST);
-                    n = fill_native(w, crc, member_bytes);
+                    std::string why;
+                    if (parallel) {
+                        n = fill_parallel(w);
+                        if (n == -1) {
+                            {
+                                std::lock_guard<std::mutex> lk(mu);
+                                if (abort_) return;              // the reader is going away, not a decoding failure
+                            }
+                            why = pinflater.error();
+                            pinflater.stop();
+                            parallel = false;
+                            if (blocks[w].size() < HIST + BLOCK + 64) blocks[w].resize(HIST + BLOCK + 64);
+                        }
+                    } else {
+                        // the last 32 KiB of the previous block are the window of the next one
+                        if (delivered) memcpy(blocks[w].data(), text(w ^ 1) + BLOCK - HIST, HIST);
+                        n = fill_native(w, crc, member_bytes);
+                        if (n == -1) why = inflater.error();
+                    }
                     if (n == -1) {
                         // The native decoder gave up (a stream it does not understand): hand the file to zlib, skip
                         // what the parser already has, and carry on from there.  Corrupt data fails in zlib as well.
                         native = false;
-                        std::string why = inflater.error();
                         gz = gzopen(path_.c_str(), "rb");
                         n = -3;
                         if (gz) {
@@ -286,7 +359,7 @@ struct LineSource {
                     if (n < 0 || (errnum != Z_OK && errnum != Z_STREAM_END))
                         error_ = path_ + ": " + (msg && *msg ? msg : "gzip stream is damaged or cut short");
                 }
-                const bool last = n <= 0 || (native && (size_t)n < BLOCK);
+                const bool last = n <= 0 || (native && !parallel && (size_t)n < BLOCK);
                 {
                     std::lock_guard<std::mutex> lk(mu);
                     lens[w] = n > 0 ? (size_t)n : 0;
@@ -421,9 +494,26 @@ struct LineSource {
                 abort_ = true;
             }
             cv.notify_all();
+            pinflater.stop();              // a worker blocked in the parallel decoder's next() wakes up with a failure
             worker.join();
         }
         if (gz) gzclose(gz);
+        if (counted_) --g_active_readers;
+        size_t c = 0, f = 0, a = 0;
+        pinflater.stats(&c, &f, &a);
+        t_reader_stats[0] = c ? (parallel ? 2 : 3) : (native ? 1 : 0);
+        t_reader_stats[1] = (int64_t)c;
+        t_reader_stats[2] = (int64_t)f;
+        t_reader_stats[3] = (int64_t)a;
+        if (getenv("EPI_INFLATE_DEBUG") != nullptr) {
+            fprintf(stderr, "[epi reader] %s: %s, %zu chunks, %zu with a start, %zu accepted, %llu bytes delivered\n", path_.c_str(),
+                    c ? (parallel ? "parallel inflate" : "parallel inflate abandoned") : (native ? "sequential inflate" : "zlib"), c, f, a,
+                    (unsigned long long)delivered);
+            if (c)
+                fprintf(stderr, "[epi reader]   pool time: decode %.3f s, waiting for the predecessor %.3f s, resolve %.3f s, crc %.3f s\n",
+                        pinflater.us_decode.load() * 1e-6, pinflater.us_wait.load() * 1e-6, pinflater.us_resolve.load() * 1e-6,
+                        pinflater.us_crc.load() * 1e-6);
+        }
     }
 };
 
@@ -540,6 +630,12 @@ extern "C" int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int
     return 0;
 }
 
+extern "C" int epi_reader_stats(int64_t* out4) {
+    EPI_REQUIRE(out4 != nullptr, "null pointer argument");
+    for (int i = 0; i < 4; ++i) out4[i] = t_reader_stats[i];
+    return 0;
+}
+
 extern "C" int epi_pack_tsv(const char* path, int64_t row_lo, int64_t row_hi, int32_t cols, int32_t num_states,
                             int8_t* out, int64_t pitch, int64_t* starts, int64_t* ends, int32_t* chrom_id,
                             char* chrom_names, int32_t chrom_names_cap, int32_t* n_chrom_out) {
@@ -582,7 +678,7 @@ struct ParsedFile {
     static constexpr int64_t CHUNK_ROWS = 1 << 15;
     int32_t cols = 0;
     int64_t rows = 0;
-    std::vector<std::vector<int8_t>> labels;      // chunks of CHUNK_ROWS x cols
+    std::vector<std::unique_ptr<int8_t[]>> labels;      // chunks of CHUNK_ROWS x cols, not zero-filled: first touched by the parser threads
     std::vector<int64_t> starts, ends;
     std::vector<int32_t> chrom;
     std::vector<std::string> names;
@@ -591,15 +687,12 @@ struct ParsedFile {
 
 // Number of parser threads for one file: the inflate thread of every file being read plus its parsers should fit the
 // machine, so a single file gets up to four parsers and a directory read file-parallel (session.prefetch) one per file.
-static std::atomic<int> g_active_parses{0};
 static int parse_threads() {
     if (const char* e = getenv("EPI_PARSE_THREADS")) {
         const int v = atoi(e);
         if (v >= 1) return v > 16 ? 16 : v;
     }
-    const int cores = (int)std::thread::hardware_concurrency();
-    const int active = std::max(1, g_active_parses.load());
-    return std::max(1, std::min(4, cores / active - 1));
+    return std::max(1, std::min(8, epi::cores_per_reader() / 2));
 }
 
 extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out,
@@ -608,10 +701,6 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
     EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
     LineSource src;
     EPI_REQUIRE(src.open(path), "cannot open %s", path);
-    struct ActiveGuard {
-        ActiveGuard() { ++g_active_parses; }
-        ~ActiveGuard() { --g_active_parses; }
-    } guard;
     std::unique_ptr<ParsedFile> pf(new ParsedFile());
     std::vector<std::pair<const char*, const char*>> lines;
     int last_id = -1;
@@ -619,7 +708,13 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
     // names resolved (serial: the name table grows), and the rows -- whose indices, hence destinations, are known by now --
     // parsed by a few threads.  Parsing (4 ns per label) was the slower of the two pipelined stages; with it spread out
     // the single-stream inflate bounds the read.
+    const bool dbg_t = getenv("EPI_INFLATE_DEBUG") != nullptr;
+    double t_wait = 0, t_prep = 0, t_parse = 0;
+    auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tq = now_s();
     while (src.next_batch(lines)) {
+        double tb = now_s();
+        t_wait += tb - tq;
         const int64_t n = (int64_t)lines.size(), r0 = pf->rows;
         if (r0 == 0) {
             int tabs = 0;
@@ -628,7 +723,7 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
             EPI_REQUIRE(pf->cols >= 1, "%s: expected `chr start end state_1 ...` rows", path);
         }
         while ((int64_t)pf->labels.size() * ParsedFile::CHUNK_ROWS < r0 + n)
-            pf->labels.emplace_back((size_t)ParsedFile::CHUNK_ROWS * pf->cols);
+            pf->labels.emplace_back(new int8_t[(size_t)ParsedFile::CHUNK_ROWS * pf->cols]);
         pf->starts.resize((size_t)(r0 + n));
         pf->ends.resize((size_t)(r0 + n));
         pf->chrom.resize((size_t)(r0 + n));
@@ -649,6 +744,8 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
             }
             pf->chrom[(size_t)(r0 + i)] = last_id = id;
         }
+        double tc = now_s();
+        t_prep += tc - tb;
         const int nt = (int)std::min<int64_t>(parse_threads(), std::max<int64_t>(1, n / 256));
         std::vector<std::string> errs((size_t)nt);
         std::vector<int64_t> err_row((size_t)nt, -1);
@@ -658,7 +755,7 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
             int32_t cid = 0;
             for (int64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
                 const int64_t r = r0 + i;
-                int8_t* dst = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+                int8_t* dst = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].get() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
                 if (parse_row(path, r, lines[(size_t)i].first, lines[(size_t)i].second, pf->cols, num_states, dst,
                               &pf->starts[(size_t)r], &pf->ends[(size_t)r], &cid, no_names, no_last, false)) {
                     errs[(size_t)t] = epi_last_error();        // the message lives in this thread's error slot
@@ -680,7 +777,10 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
                 return 2;
             }
         pf->rows = r0 + n;
+        tq = now_s();
+        t_parse += tq - tc;
     }
+    if (dbg_t) fprintf(stderr, "[epi reader] parse loop: waiting for text %.3f s, line split + ids %.3f s, row parse %.3f s\n", t_wait, t_prep, t_parse);
     EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     size_t nb = 0;
     for (const std::string& s : pf->names) nb += s.size() + 1;
@@ -700,7 +800,7 @@ extern "C" int epi_tsv_parse_fetch(void* handle, int64_t row_lo, int64_t row_hi,
                 (long long)row_lo, (long long)row_hi, (long long)pf->rows);
     EPI_REQUIRE(row_hi == row_lo || (out != nullptr && pitch >= pf->cols), "bad output buffer");
     for (int64_t r = row_lo; r < row_hi; ++r) {
-        const int8_t* src = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].data() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+        const int8_t* src = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].get() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
         int8_t* dst = out + (r - row_lo) * pitch;
         memcpy(dst, src, (size_t)pf->cols);
         if (pitch > pf->cols) memset(dst + pf->cols, 0, (size_t)(pitch - pf->cols));

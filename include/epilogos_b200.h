@@ -220,9 +220,14 @@ int epi_paired_host(const int8_t* xa_host, int64_t pitch_a, int32_t cols_a, cons
  *                     staging area and reports rows / columns / chromosome names; _fetch copies a row range into the
  *                     caller's (pinned) buffers exactly as epi_pack_tsv would have written them; _close frees it. */
 /* Diagnostic: the decompressed byte stream the parsers see for `path` (gzip through the library's own DEFLATE decoder,
- * csrc/fast_inflate.h, with CRC-32 / ISIZE checks per member; zlib with EPI_ZLIB_INFLATE=1; plain files as they are).
+ * csrc/fast_inflate.h, with CRC-32 / ISIZE checks per member -- large files on several threads at once,
+ * csrc/parallel_inflate.h; zlib with EPI_ZLIB_INFLATE=1; plain files as they are).
  * Copies at most cap bytes to out (NULL allowed); *n_out = total length. */
 int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int64_t* n_out);
+/* Diagnostic: how the calling thread's last finished read was inflated.  out4[0] = 0 zlib / plain file, 1 the sequential
+ * native decoder, 2 the parallel decoder, 3 the parallel decoder gave up midway (zlib finished the file);
+ * out4[1..3] = chunks of the compressed file, chunks in which a block / member start was found, chunks accepted. */
+int epi_reader_stats(int64_t* out4);
 int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
 int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out, int32_t* cols_out,
                        int32_t* n_chrom_out, int32_t* names_bytes_out);

@@ -1,11 +1,15 @@
 """Native host I/O (epi_pack_tsv / epi_write_scores_gz / epi_tsv_shape): no GPU needed."""
 import gzip
+import sys
+from pathlib import Path
 
 import numpy as np
 import pytest
 
 from epilogos_b200 import helpers, writer
 from epilogos_b200._lib import EpilogosB200Error
+
+ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_writer_matches_python_format_on_edge_values(tmp_path):
@@ -253,6 +257,178 @@ def test_native_inflate_reads_the_writers_multi_member_files_across_blocks(tmp_p
     monkeypatch.delenv("EPI_ZLIB_INFLATE", raising=False)
     _, got = helpers.read_scores(p)
     assert got.shape == (rows, k) and np.array_equal(got[::997], np.array([[float("%.5f" % float(v)) for v in r] for r in sc[::997]]))
+
+
+# ---- one gzip stream decoded by several threads (csrc/parallel_inflate.h) --------------------------------------------
+def _reader_stats():
+    import ctypes
+    from epilogos_b200 import _lib
+    out = (ctypes.c_int64 * 4)()
+    _lib.call("epi_reader_stats", out)
+    return list(out)            # mode (2 = parallel), chunks, chunks with a start, chunks accepted
+
+
+def _matrix_text(rng, rows, cols, k=18, dominant=0.6):
+    x = rng.integers(1, k + 1, size=(rows, cols))
+    x[rng.random((rows, cols)) < dominant] = k
+    return b"".join(b"chr1\t%d\t%d\t" % (i * 200, i * 200 + 200) + b"\t".join(str(int(v)).encode() for v in r) + b"\n"
+                    for i, r in enumerate(x))
+
+
+def _bgzf(data, block=60000, level=6):
+    """bgzip's container: independent members of at most 64 KiB with an FEXTRA 'BC' subfield holding the member size."""
+    import struct
+    import zlib
+    out = b""
+    for i in range(0, max(len(data), 1), block):
+        piece = data[i:i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = co.compress(piece) + co.flush()
+        bsize = 12 + 6 + len(raw) + 8 - 1
+        out += b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) + raw + \
+            struct.pack("<II", zlib.crc32(piece), len(piece) & 0xffffffff)
+    return out + b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 27) + \
+        b"\x03\0" + b"\0" * 8                                                     # bgzip's empty end-of-file member
+
+
+def test_parallel_inflate_equals_the_data_for_every_stream_shape(tmp_path, monkeypatch):
+    """Chunks of the compressed file decoded concurrently from block / member starts found by inspection, with unknown
+    history as markers, chained and resolved in order: the text must be the data for label matrices, low-entropy and
+    literal-only streams, runs with short periods, stored and fixed blocks in between, flush points, multi-member and bgzip
+    files, for chunks much smaller than, comparable to and larger than a DEFLATE block, and the parallel path must
+    actually have been taken for the well-conditioned ones."""
+    import zlib
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"0123456789\t\n", dtype=np.uint8)
+    matrix = _matrix_text(rng, 12000, 60)
+    cases = {
+        "matrix": matrix,
+        "lowentropy": rng.choice(alphabet, 1_500_000, p=[.3, .2, .1, .05, .05, .05, .05, .04, .03, .03, .08, .02]).tobytes(),
+        "random": rng.integers(0, 256, 400000, dtype=np.uint8).tobytes(),
+        "runs": b"a" * 70000 + b"ab" * 40000 + b"abc" * 30000 + b"abcdefg" * 20000 + bytes(range(256)) * 3000 + matrix[:300000],
+        "mixed": matrix[:400000] + rng.integers(0, 256, 150000, dtype=np.uint8).tobytes() + b"\0" * 300000 + matrix[400000:900000],
+    }
+    taken = {}
+    for name, data in cases.items():
+        variants = {"l1": gzip.compress(data, 1), "l6": gzip.compress(data, 6), "l9": gzip.compress(data, 9)}
+        step = len(data) // 3 + 1
+        variants["members3"] = b"".join(gzip.compress(data[i:i + step], 6) for i in range(0, len(data), step))
+        variants["bgzf"] = _bgzf(data)
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)
+        out = b""
+        for j, i in enumerate(range(0, len(data), 50021)):
+            out += co.compress(data[i:i + 50021]) + co.flush(zlib.Z_SYNC_FLUSH if j % 2 else zlib.Z_FULL_FLUSH)
+        variants["flush"] = out + co.flush() + b"\0" * 19
+        co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, zlib.Z_FIXED)
+        variants["fixed"] = co.compress(data) + co.flush()
+        for tag, packed in variants.items():
+            p = tmp_path / ("%s_%s.gz" % (name, tag))
+            p.write_bytes(packed)
+            for chunk, threads in ((1500, 3), (20000, 2), (20000, 5), (150000, 4)):
+                monkeypatch.setenv("EPI_INFLATE_CHUNK", str(chunk))
+                monkeypatch.setenv("EPI_INFLATE_THREADS", str(threads))
+                assert _inflate(p, monkeypatch) == data, (name, tag, chunk, threads)
+                st = _reader_stats()
+                assert st[0] in (1, 2), (name, tag, chunk, threads, st)          # never the zlib fall-back on valid input
+                taken[(name, tag, chunk)] = st
+            p.unlink()
+    # dynamic-Huffman streams cut into chunks of a few blocks: every chunk has a start and every chunk is accepted
+    for name in ("matrix", "lowentropy", "mixed"):
+        for tag in ("l6", "l9", "members3", "bgzf"):
+            st = taken[(name, tag, 150000)]
+            assert st[0] == 2 and st[1] >= 2 and st[3] >= st[1] - 1, (name, tag, st)
+    assert taken[("matrix", "fixed", 20000)][0] == 1                             # fixed blocks only: nothing to start from
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "1")                               # one thread: the sequential decoder
+    p = tmp_path / "seq.gz"
+    p.write_bytes(gzip.compress(matrix, 6))
+    assert _inflate(p, monkeypatch) == matrix and _reader_stats()[0] == 1
+
+
+def test_parallel_inflate_is_not_fooled_by_embedded_streams(tmp_path, monkeypatch):
+    """The finder looks at raw bytes, so a stored block that holds another gzip file makes it find member and block starts
+    that are not starts of THIS stream; a chunk is only accepted where the previous accepted chunk ended, so the text is
+    still the data."""
+    rng = np.random.default_rng(12)
+    inner = gzip.compress(_matrix_text(rng, 6000, 40), 6)
+    blob = b"".join(rng.integers(0, 256, 3000, dtype=np.uint8).tobytes() + inner for _ in range(4))
+    for level in (0, 6):                                            # stored outright / stored because incompressible
+        p = tmp_path / ("outer%d.gz" % level)
+        p.write_bytes(gzip.compress(blob, level))
+        for chunk in (5000, 40000):
+            monkeypatch.setenv("EPI_INFLATE_CHUNK", str(chunk))
+            monkeypatch.setenv("EPI_INFLATE_THREADS", "4")
+            assert _inflate(p, monkeypatch) == blob, (level, chunk)
+    # a real stream followed by stored blocks with embedded streams: parallel mode is taken and false starts are dropped
+    data = _matrix_text(rng, 15000, 40) + blob + _matrix_text(rng, 8000, 40)
+    p = tmp_path / "both.gz"
+    p.write_bytes(gzip.compress(data, 6))
+    monkeypatch.setenv("EPI_INFLATE_CHUNK", "30000")
+    assert _inflate(p, monkeypatch) == data
+    st = _reader_stats()
+    assert st[0] == 2 and st[3] < st[2], st                         # some chunk starts were found and NOT accepted
+
+
+def test_parallel_inflate_rejects_damaged_streams(tmp_path, monkeypatch):
+    """Cut, CRC, length and data damage, garbage after the last member and seeded single-bit flips with the parallel
+    decoder switched on for a small file: an error or the exact text, never different text."""
+    rng = np.random.default_rng(13)
+    text = _matrix_text(rng, 9000, 40)
+    good = gzip.compress(text, 6)
+    assert len(good) > 100000
+    monkeypatch.setenv("EPI_INFLATE_CHUNK", "30000")
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "3")
+    p = tmp_path / "m.txt.gz"
+    p.write_bytes(good)
+    assert _inflate(p, monkeypatch) == text and _reader_stats()[0] == 2
+    loc, states = helpers.read_matrix(p, num_states=18)
+    assert states.shape == (9000, 40)
+    third = len(good) // 3
+    damaged = {"cut in the data": good[:len(good) // 2], "cut in the trailer": good[:-3],
+               "crc": good[:-8] + bytes([good[-8] ^ 1]) + good[-7:], "length": good[:-1] + bytes([good[-1] ^ 0x40]),
+               "data": good[:third] + bytes([good[third] ^ 0x10]) + good[third + 1:],
+               "garbage": good + b"this is not gzip data, 1234567890 1234567890"}
+    for what, blob in damaged.items():
+        p.write_bytes(blob)
+        with pytest.raises(EpilogosB200Error):
+            _inflate(p, monkeypatch)
+        with pytest.raises(EpilogosB200Error):
+            helpers.read_matrix(p, num_states=18)
+    p.write_bytes(good + b"\0" * 100 + b"")
+    assert _inflate(p, monkeypatch) == text                        # zero padding is tolerated, as by Python's gzip module
+    p.write_bytes(good + good)
+    assert _inflate(p, monkeypatch) == text + text
+    for trial in range(200):
+        blob = bytearray(good)
+        i = int(rng.integers(2, len(blob)))
+        blob[i] ^= 1 << int(rng.integers(0, 8))
+        p.write_bytes(bytes(blob))
+        try:
+            got = _inflate(p, monkeypatch)
+        except EpilogosB200Error:
+            continue
+        assert got == text, "byte %d flipped: accepted with different content" % i
+
+
+def test_parallel_and_sequential_readers_parse_the_same_matrix(tmp_path, monkeypatch):
+    """read_matrix over a file large enough for the parallel decoder by default (no knobs): same labels and coordinates as
+    with one inflate thread, and as the matrix that was written."""
+    rng = np.random.default_rng(14)
+    x = rng.integers(0, 18, size=(60000, 300)).astype(np.int8)
+    x[rng.random(x.shape) < 0.5] = 17
+    p = tmp_path / "epilogos_matrix_chr1.txt.gz"
+    sys.path.insert(0, str(ROOT))
+    from oracle import reference_driver as ref
+    ref.write_matrix_tsv_gz(p, x, level=6)
+    assert p.stat().st_size > (2 << 20)
+    monkeypatch.delenv("EPI_INFLATE_CHUNK", raising=False)
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "4")
+    loc_p, got_p = helpers.read_matrix(p, num_states=18)
+    assert _reader_stats()[0] == 2
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "1")
+    loc_s, got_s = helpers.read_matrix(p, num_states=18)
+    assert _reader_stats()[0] == 1
+    assert np.array_equal(got_p, x) and np.array_equal(got_s, x)
+    assert np.array_equal(loc_p["start"], loc_s["start"]) and np.array_equal(loc_p["end"], np.arange(1, 60001) * 200)
 
 
 def _pack_reference(x, cols, bits):
