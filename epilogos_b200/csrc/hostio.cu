@@ -799,11 +799,23 @@ extern "C" int epi_tsv_parse_fetch(void* handle, int64_t row_lo, int64_t row_hi,
     EPI_REQUIRE(row_lo >= 0 && row_hi >= row_lo && row_hi <= pf->rows, "row range [%lld, %lld) outside the %lld parsed rows",
                 (long long)row_lo, (long long)row_hi, (long long)pf->rows);
     EPI_REQUIRE(row_hi == row_lo || (out != nullptr && pitch >= pf->cols), "bad output buffer");
-    for (int64_t r = row_lo; r < row_hi; ++r) {
-        const int8_t* src = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].get() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
-        int8_t* dst = out + (r - row_lo) * pitch;
-        memcpy(dst, src, (size_t)pf->cols);
-        if (pitch > pf->cols) memset(dst + pf->cols, 0, (size_t)(pitch - pf->cols));
+    auto copy_rows = [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; ++r) {
+            const int8_t* src = pf->labels[(size_t)(r / ParsedFile::CHUNK_ROWS)].get() + (r % ParsedFile::CHUNK_ROWS) * pf->cols;
+            int8_t* dst = out + (r - row_lo) * pitch;
+            memcpy(dst, src, (size_t)pf->cols);
+            if (pitch > pf->cols) memset(dst + pf->cols, 0, (size_t)(pitch - pf->cols));
+        }
+    };
+    // large matrices: the copy into the caller's (possibly freshly allocated, not yet touched) buffer on a few threads
+    const int64_t nrows = row_hi - row_lo;
+    const int nt = nrows * pitch >= (32ll << 20) ? parse_threads() : 1;
+    if (nt <= 1) {
+        copy_rows(row_lo, row_hi);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(copy_rows, row_lo + nrows * t / nt, row_lo + nrows * (t + 1) / nt);
+        for (auto& th : pool) th.join();
     }
     const size_t n = (size_t)(row_hi - row_lo);
     if (starts && n) memcpy(starts, pf->starts.data() + row_lo, n * sizeof(int64_t));
