@@ -11,6 +11,7 @@
 //                        members (a valid multi-member .gz; the decompressed text is byte-identical to the
 //                        reference's)
 #include <math.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,12 +38,18 @@ namespace epi {
 // at once (session.prefetch) and, under torchrun, several ranks share the host (LOCAL_WORLD_SIZE), so the machine's
 // cores are divided by both before a reader takes its share.
 static std::atomic<int> g_active_readers{0};
+static std::atomic<int> g_expected_readers{0};      // epi_reader_concurrency: files the caller is about to read at once
 static int cores_per_reader() {
     int cores = (int)std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = std::min(cores > 0 ? cores : 1 << 20, CPU_COUNT(&set));
+#endif
     if (cores < 1) cores = 1;
     int ranks = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-    const int active = std::max(1, g_active_readers.load());
+    const int active = std::max(1, std::max(g_active_readers.load(), g_expected_readers.load()));
     return std::max(1, cores / (ranks * active));
 }
 // what the calling thread's last reader did (epi_reader_stats): mode, chunks, chunks with a start, chunks accepted
@@ -627,6 +634,11 @@ extern "C" int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int
     }
     EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     *n_out = total;
+    return 0;
+}
+
+extern "C" int epi_reader_concurrency(int32_t files) {
+    g_expected_readers.store(files > 0 ? files : 0);
     return 0;
 }
 

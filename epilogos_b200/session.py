@@ -105,8 +105,8 @@ def load_shard(file1, file2, num_states, backend=None, keep=None):
 
 def prefetch(pairs, num_states, backend=None, workers=None):
     """Parse this rank's rows of ALL input files concurrently, before the stages run.  The reference parses every file
-    again in every stage and worker; the native packer (csrc/hostio.cu) releases the GIL and uses two threads per file
-    (inflate | parse), so a whole-genome directory of per-chromosome files is read in the time of its largest files
+    again in every stage and worker; the native packer (csrc/hostio.cu) releases the GIL and gives every file its share of
+    the cores (inflate | parse threads), so a whole-genome directory of per-chromosome files is read in the time of its largest files
     instead of their sum.  The cache is sized to hold every file, so the score stage re-uses the parsed matrices and the
     device-resident counts of the expected stage."""
     import os
@@ -120,8 +120,13 @@ def prefetch(pairs, num_states, backend=None, workers=None):
     be = get_backend(backend)
     rank, world = dist.rank(), dist.world_size()          # resolved on the calling thread
     workers = workers or max(1, min(len(todo), (os.cpu_count() or 2) // 2))
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        shards = list(pool.map(lambda p: Shard(p[0], p[1], num_states, be, rank=rank, world=world), todo))
+    from . import _lib
+    _lib.call("epi_reader_concurrency", int(workers))     # every reader takes 1/workers of this rank's cores from the start
+    try:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            shards = list(pool.map(lambda p: Shard(p[0], p[1], num_states, be, rank=rank, world=world), todo))
+    finally:
+        _lib.call("epi_reader_concurrency", 0)
     for (f, f2), sh in zip(todo, shards):
         _cache[_key(f, f2)] = sh
 
