@@ -39,6 +39,7 @@ namespace epi {
 // cores are divided by both before a reader takes its share.
 static std::atomic<int> g_active_readers{0};
 static std::atomic<int> g_expected_readers{0};      // epi_reader_concurrency: files the caller is about to read at once
+static std::atomic<int> g_reading_ranks{0};         // ... and ranks of this host that read at the same time (0: all of them)
 static int cores_per_reader() {
     int cores = (int)std::thread::hardware_concurrency();
 #ifdef __linux__
@@ -49,6 +50,7 @@ static int cores_per_reader() {
     if (cores < 1) cores = 1;
     int ranks = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    if (g_reading_ranks.load() > 0) ranks = std::min(ranks, g_reading_ranks.load());
     const int active = std::max(1, std::max(g_active_readers.load(), g_expected_readers.load()));
     return std::max(1, cores / (ranks * active));
 }
@@ -637,8 +639,9 @@ extern "C" int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int
     return 0;
 }
 
-extern "C" int epi_reader_concurrency(int32_t files) {
+extern "C" int epi_reader_concurrency(int32_t files, int32_t ranks) {
     g_expected_readers.store(files > 0 ? files : 0);
+    g_reading_ranks.store(ranks > 0 ? ranks : 0);
     return 0;
 }
 

@@ -73,6 +73,38 @@ def gather_rows(t, total_rows, dst=0):
     return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0)
 
 
+def deal_rows(full, ranges, src, pitch, pinned=False):
+    """Rank `src` holds `full`, an int8 [total, pitch] numpy matrix; every rank gets its rows ranges[rank] = (lo, hi) as an
+    int8 [hi - lo, pitch] numpy matrix (pinned when asked).  Point-to-point sends in rank order (NCCL: through the GPUs,
+    i.e. one upload on the reader and NVLink to the peers; gloo: host tensors)."""
+    import numpy as np
+    me = dist.get_rank()
+    lo, hi = ranges[me]
+    cuda = dist.get_backend() == "nccl"
+
+    def alloc(n):
+        if pinned:
+            return torch.empty((n, pitch), dtype=torch.int8, pin_memory=True)
+        return torch.empty((n, pitch), dtype=torch.int8)
+    mine = alloc(hi - lo)
+    if me == src:
+        t = torch.from_numpy(full)
+        dev = t.cuda(non_blocking=True) if cuda else t
+        for dst, (a, b) in enumerate(ranges):
+            if dst != src and b > a:
+                dist.send(dev[a:b], dst=dst)
+        mine.copy_(t[lo:hi])
+    elif hi > lo:
+        if cuda:
+            buf = torch.empty((hi - lo, pitch), dtype=torch.int8, device="cuda")
+            dist.recv(buf, src=src)
+            mine.copy_(buf)
+        else:
+            dist.recv(mine, src=src)
+    out = mine.numpy()
+    return out if isinstance(out, np.ndarray) else np.asarray(out)
+
+
 def init_from_env():
     """Join the NCCL process group when launched by torchrun (RANK / WORLD_SIZE / LOCAL_RANK in the environment):
     one process per GPU, pinned to the GPU's NUMA node.  A plain `python` launch stays single-rank."""

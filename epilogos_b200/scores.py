@@ -70,6 +70,8 @@ def _gather_locations(shard):
     """Locations of all rows on rank 0 (each rank parsed only its own row range)."""
     if dist.world_size() == 1:
         return shard.loc
+    if shard.reader is not None:                 # the rows were dealt by one reader: rank 0 got every location with them
+        return shard.loc_full if dist.rank() == 0 else None
     import torch.distributed as td
     parts = [None] * dist.world_size() if dist.rank() == 0 else None
     td.gather_object(shard.loc, parts, dst=0)

@@ -4,6 +4,8 @@ The reference re-parses every input file in every stage and in every worker (hel
 rank's row range of a file is parsed once, packed to int8, counted once on the GPU, and the device-resident
 counts (2K bytes per bin) are reused by the score stage of the same process.
 """
+import os
+import zlib
 from pathlib import Path
 
 import numpy as np
@@ -32,17 +34,73 @@ def get_backend(backend=None):
     return _backend
 
 
+def one_reader():
+    """With the rows of a file sharded over several ranks, ONE rank reads the file and deals the row ranges to the others
+    (default), instead of every rank inflating and parsing the whole file to keep its 1/N of the rows
+    (EPILOGOS_B200_READ=redundant: the behaviour up to round 2, no exchange of rows)."""
+    return os.environ.get("EPILOGOS_B200_READ", "deal") != "redundant"
+
+
+def reader_of(file1, world):
+    """The rank that reads a file when nobody assigned one: spread by file name, the same on every rank."""
+    return zlib.crc32(Path(file1).name.encode()) % world
+
+
+def _pack_locations(loc):
+    """Locations in a form that pickles in no time: coordinates as they are, chromosome names run-length encoded."""
+    chrom = np.asarray(loc["chrom"], dtype=object)
+    n = len(chrom)
+    if n == 0:
+        return dict(start=loc["start"], end=loc["end"], names=[], runs=[])
+    change = np.flatnonzero(chrom[1:] != chrom[:-1]) + 1
+    first = np.concatenate(([0], change))
+    length = np.diff(np.concatenate((first, [n])))
+    return dict(start=np.asarray(loc["start"]), end=np.asarray(loc["end"]), names=[str(chrom[i]) for i in first],
+                runs=[int(v) for v in length])
+
+
+def _unpack_locations(packed):
+    chrom = np.empty(sum(packed["runs"]), dtype=object)
+    at = 0
+    for name, run in zip(packed["names"], packed["runs"]):
+        chrom[at:at + run] = name
+        at += run
+    return dict(chrom=chrom, start=packed["start"], end=packed["end"])
+
+
 class Shard:
     """The rows [lo, hi) of one input file (or file pair) owned by this rank."""
 
-    def __init__(self, file1, file2, num_states, backend, rank=0, world=0):
+    def __init__(self, file1, file2, num_states, backend, rank=0, world=0, reader=None, exchange=True):
         self.backend = get_backend(backend)
         self.num_states = num_states
         if not Path(file1).is_file():
             raise FileNotFoundError(str(file1))
-        # one pass over the file: the row count comes out of the parse, this rank's range is cut from the parsed rows
         pinned = getattr(self.backend, "name", "") == "cuda"
         split = (rank, world) if world else (dist.rank(), dist.world_size())
+        self._counts = {}
+        self._states_dev = None
+        self.reader = None            # the rank that read the file when the rows were dealt (one_reader); else None
+        self.loc_full = None          # locations of ALL rows, on rank 0, when the rows were dealt
+        if split[1] > 1 and one_reader():
+            # ---- one reader per file: no file is inflated or parsed more than once, whatever the number of ranks
+            self.reader = reader_of(file1, split[1]) if reader is None else int(reader)
+            self._split, self._pinned, self._paired = split, pinned, str(file2) != "null"
+            self._full = None
+            if split[0] == self.reader:
+                loc, a, total = helpers.read_matrix(file1, None, want_locations=True, num_states=num_states, pinned=pinned,
+                                                    return_total=True)
+                b = None
+                if self._paired:
+                    _, b = helpers.read_matrix(file2, None, want_locations=False, num_states=num_states, pinned=pinned)
+                    if b.shape[0] != a.shape[0]:
+                        raise ValueError("paired input files must have the same number of rows")
+                self._full = (loc, a, b, total)
+            if exchange:
+                self.exchange()
+            return
+        # ---- every rank reads the file itself.  One pass: the row count comes out of the parse, this rank's range is cut
+        # from the parsed rows
         self.loc, self.states_a, self.total_rows = helpers.read_matrix(file1, None, want_locations=True,
                                                                        num_states=num_states, pinned=pinned,
                                                                        split=split, return_total=True)
@@ -53,8 +111,43 @@ class Shard:
             _, self.states_b = helpers.read_matrix(file2, rows, want_locations=False, num_states=num_states)
             if self.states_b.shape[0] != self.states_a.shape[0]:
                 raise ValueError("paired input files must have the same number of rows")
-        self._counts = {}
-        self._states_dev = None
+
+    def exchange(self):
+        """Collective (every rank, same order of files): the reader announces the shape, deals the row ranges of
+        helpers.splitRows to the ranks and hands the locations to rank 0, which writes the outputs."""
+        import torch.distributed as td
+        rank, world = self._split
+        meta = [None]
+        if rank == self.reader:
+            loc, a, b, total = self._full
+            meta = [(int(total), int(a.shape[1]), int(b.shape[1]) if b is not None else -1)]
+        td.broadcast_object_list(meta, src=self.reader)
+        total, cols_a, cols_b = meta[0]
+        ranges = helpers.splitRows(total, world)
+        self.total_rows = total
+        self.lo, self.hi = ranges[rank]
+        full_a = full_b = None
+        if rank == self.reader:
+            full_a = a.base if isinstance(a.base, np.ndarray) and a.base.shape[0] == a.shape[0] else np.ascontiguousarray(a)
+            if b is not None:
+                full_b = b.base if isinstance(b.base, np.ndarray) and b.base.shape[0] == b.shape[0] else np.ascontiguousarray(b)
+        self.states_a = dist.deal_rows(full_a, ranges, self.reader, helpers.pitch_for(max(cols_a, 1)), self._pinned)[:, :cols_a]
+        self.states_b = None
+        if cols_b >= 0:
+            self.states_b = dist.deal_rows(full_b, ranges, self.reader, helpers.pitch_for(max(cols_b, 1)), self._pinned)[:, :cols_b]
+        # locations: only the writing rank needs them
+        self.loc = None
+        if self.reader == 0:
+            if rank == 0:
+                self.loc_full = {k: loc[k] for k in ("chrom", "start", "end")}
+        else:
+            box = [_pack_locations(loc)] if rank == self.reader else [None]
+            if rank == self.reader:
+                td.send_object_list(box, dst=0)
+            elif rank == 0:
+                td.recv_object_list(box, src=self.reader)
+                self.loc_full = _unpack_locations(box[0])
+        self._full = None
 
     @property
     def paired(self):
@@ -99,18 +192,28 @@ def load_shard(file1, file2, num_states, backend=None, keep=None):
     if key not in _cache:
         while len(_cache) >= (keep or _keep):
             _cache.pop(next(iter(_cache)))
-        _cache[key] = Shard(file1, file2, num_states, backend)
+        if dist.world_size() > 1 and one_reader():
+            from . import _lib
+            _lib.call("epi_reader_concurrency", 1, 1)      # one rank reads this file: it may use the whole host
+            try:
+                _cache[key] = Shard(file1, file2, num_states, backend)
+            finally:
+                _lib.call("epi_reader_concurrency", 0, 0)
+        else:
+            _cache[key] = Shard(file1, file2, num_states, backend)
     return _cache[key]
 
 
 def prefetch(pairs, num_states, backend=None, workers=None):
-    """Parse this rank's rows of ALL input files concurrently, before the stages run.  The reference parses every file
-    again in every stage and worker; the native packer (csrc/hostio.cu) releases the GIL and gives every file its share of
-    the cores (inflate | parse threads), so a whole-genome directory of per-chromosome files is read in the time of its largest files
-    instead of their sum.  The cache is sized to hold every file, so the score stage re-uses the parsed matrices and the
-    device-resident counts of the expected stage."""
-    import os
+    """Parse the input files concurrently and once, before the stages run.  The reference parses every file again in every
+    stage and worker; the native packer (csrc/hostio.cu) releases the GIL and gives every file its share of the cores
+    (inflate | parse threads), so a whole-genome directory of per-chromosome files is read in the time of its largest
+    files instead of their sum.  With the rows sharded over several ranks the files are dealt to the ranks as READERS by
+    size (largest first, round robin); every reader then deals the row ranges of its files to all ranks, so no file is
+    read twice and every rank still holds 1/N of every file.  The cache is sized to hold every file, so the score stage
+    re-uses the parsed matrices and the device-resident counts of the expected stage."""
     from concurrent.futures import ThreadPoolExecutor
+    from . import _lib
     global _keep
     pairs = list(pairs)
     _keep = max(_keep, len(pairs) + 1)
@@ -119,15 +222,26 @@ def prefetch(pairs, num_states, backend=None, workers=None):
         return
     be = get_backend(backend)
     rank, world = dist.rank(), dist.world_size()          # resolved on the calling thread
-    workers = workers or max(1, min(len(todo), (os.cpu_count() or 2) // 2))
-    from . import _lib
-    _lib.call("epi_reader_concurrency", int(workers))     # every reader takes 1/workers of this rank's cores from the start
+    dealt = world > 1 and one_reader()
+    readers = [None] * len(todo)
+    mine = len(todo)
+    if dealt:
+        order = sorted(range(len(todo)), key=lambda i: (-Path(todo[i][0]).stat().st_size, str(todo[i][0])))
+        for j, i in enumerate(order):
+            readers[i] = j % world
+        mine = sum(1 for r in readers if r == rank)
+    workers = workers or max(1, min(max(mine, 1), (os.cpu_count() or 2) // 2))
+    # every reader takes its share of the cores from the start; with dealt files only min(world, files) ranks read at all
+    _lib.call("epi_reader_concurrency", int(min(workers, max(mine, 1))), int(min(world, len(todo))) if dealt else 0)
     try:
         with ThreadPoolExecutor(max_workers=workers) as pool:
-            shards = list(pool.map(lambda p: Shard(p[0], p[1], num_states, be, rank=rank, world=world), todo))
+            shards = list(pool.map(lambda a: Shard(a[0][0], a[0][1], num_states, be, rank=rank, world=world, reader=a[1],
+                                                   exchange=False), zip(todo, readers)))
     finally:
-        _lib.call("epi_reader_concurrency", 0)
+        _lib.call("epi_reader_concurrency", 0, 0)
     for (f, f2), sh in zip(todo, shards):
+        if sh.reader is not None:
+            sh.exchange()                                  # collectives: calling thread, same file order on every rank
         _cache[_key(f, f2)] = sh
 
 

@@ -228,9 +228,10 @@ int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int64_t* n_out
  * native decoder, 2 the parallel decoder, 3 the parallel decoder gave up midway (zlib finished the file);
  * out4[1..3] = chunks of the compressed file, chunks in which a block / member start was found, chunks accepted. */
 int epi_reader_stats(int64_t* out4);
-/* Hint: the caller is about to read `files` inputs concurrently (session.prefetch): every reader then takes its share of
- * the cores for its inflate and parser threads from the start.  0 clears the hint (readers count themselves). */
-int epi_reader_concurrency(int32_t files);
+/* Hint: the caller is about to read `files` inputs concurrently (session.prefetch) while `ranks` processes of this host
+ * read at the same time (0: all LOCAL_WORLD_SIZE of them; 1 when one rank reads for everybody): every reader then takes
+ * its share of the cores for its inflate and parser threads from the start.  (0, 0) clears the hint. */
+int epi_reader_concurrency(int32_t files, int32_t ranks);
 int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
 int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out, int32_t* cols_out,
                        int32_t* n_chrom_out, int32_t* names_bytes_out);

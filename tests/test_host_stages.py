@@ -233,11 +233,18 @@ def test_paired_pipeline_files_match_reference(tmp_path, golden, name):
 FILES_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-os.environ["EPILOGOS_B200_SHARD"] = {shard!r}
+os.environ["EPILOGOS_B200_SHARD"] = {shard!r}.split("-")[0]
+if {shard!r}.endswith("-redundant"):
+    os.environ["EPILOGOS_B200_READ"] = "redundant"
 import torch.distributed as td
 from pathlib import Path
 from fake_backend import OracleBackend
-from epilogos_b200 import dist, run
+from epilogos_b200 import dist, helpers, run
+_read, _parsed = helpers.read_matrix, []
+def _counting(path, *a, **k):
+    _parsed.append(Path(path).name)
+    return _read(path, *a, **k)
+helpers.read_matrix = _counting
 td.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 out = Path({out!r}); inp = Path({inp!r})
 pairs = [(f, "null") for f in sorted(inp.glob("*"))]
@@ -246,15 +253,18 @@ say = (lambda *a, **k: print(*a, **k, flush=True)) if lead else (lambda *a, **k:
 run.run_stages(pairs, "single", 18, 2, out, "in_s2", out / "exp_freq_in_s2.npy", 1, 17, -1, {meta!r}, 20, False, say,
                backend=OracleBackend())
 print("RANK", td.get_rank(), "files", sorted(p.name for p in out.glob("scores_*")), flush=True)
+print("PARSED", td.get_rank(), " ".join(_parsed), flush=True)
 td.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("shard", ["files", "rows"])
+@pytest.mark.parametrize("shard", ["files", "rows", "rows-redundant"])
 def test_run_stages_world_size_two_files_or_rows(tmp_path, golden, shard):
     """run.run_stages on two gloo ranks with three input files of different sizes: whole files dealt to the ranks
     (EPILOGOS_B200_SHARD=files: each rank runs the unsharded stages on its files, tables meet through the files) and rows
-    split over the ranks (default) both reproduce the single-rank result -- table, every score file, ROI list."""
+    split over the ranks (default: every file is parsed by ONE rank, which deals the row ranges to the others;
+    EPILOGOS_B200_READ=redundant: every rank parses every file) all reproduce the single-rank result -- table, every score
+    file, ROI list."""
     from oracle import epilogos_oracle as orc
     from test_cli import META
     g = golden("real10_chr1_k18")
@@ -275,6 +285,14 @@ def test_run_stages_world_size_two_files_or_rows(tmp_path, golden, shard):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     if shard == "files":
         assert "Input files dealt to the ranks: 3 files over 2 GPUs" in logs[0]
+    parsed = [line.split()[2:] for log in logs for line in log.splitlines() if line.startswith("PARSED")]
+    assert len(parsed) == 2
+    names = sorted(n for p in parsed for n in p)
+    if shard == "rows-redundant":
+        assert names == sorted(2 * [n + ".txt" for n in parts])                  # every rank parsed every file
+    else:
+        assert names == sorted(n + ".txt" for n in parts)                        # every file parsed exactly once, by one rank
+        assert all(len(p) >= 1 for p in parsed)                                   # ... and both ranks read something
     allx = np.concatenate(list(parts.values()))
     exp = orc.normalize_expected(orc.s2_expected_counts(allx, 18))
     for name, part in parts.items():
