@@ -303,7 +303,12 @@ struct LineSource {
                     least = 0;
                 }
             }
-            if (threads >= 2 && size >= least) parallel = pinflater.start(packed.data(), size, threads, chunk, HIST);
+            // a stream that expands more than ~100-fold (ISIZE of the last member against the file size) would need
+            // gigabytes per chunk in flight: such files stay with the sequential decoder and its 16 MB blocks
+            const uint64_t isize = size >= 18 ? ((uint64_t)packed[size - 4] | ((uint64_t)packed[size - 3] << 8) |
+                                                 ((uint64_t)packed[size - 2] << 16) | ((uint64_t)packed[size - 1] << 24)) : 0;
+            const bool dense = isize / 100 <= (uint64_t)size;
+            if (threads >= 2 && size >= least && dense) parallel = pinflater.start(packed.data(), size, threads, chunk, HIST);
         }
         blocks[0].resize(HIST + BLOCK + 64);
         blocks[1].resize(HIST + BLOCK + 64);

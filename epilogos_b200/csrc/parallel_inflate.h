@@ -23,6 +23,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -144,7 +145,7 @@ public:
     // (count in *n_out); every member that ends inside the chunk is recorded with its trailer.
     template <class StopFn>
     Status decode(const Start& start, StopFn stop, SymbolBuffer& out, size_t* n_out, std::vector<MemberEnd>& ends, Start* end_at,
-                  const std::atomic<bool>* abort, size_t expect_symbols) {
+                  const std::atomic<bool>* abort, size_t expect_symbols, size_t max_symbols) {
         size_t n = 0;
         *n_out = 0;
         err_ = "";
@@ -173,6 +174,7 @@ public:
             const int type = block_header(false);
             if (type < 0) return FAILED;
             for (;;) {                                       // the block's data, growing the buffer as needed
+                if (n > max_symbols) return fail_st("a chunk expands beyond the parallel decoder's memory budget");
                 if (out.cap < n + 66000 && !out.reserve(out.cap + out.cap / 2 + 66000)) return fail_st("out of memory");
                 uint16_t* o = out.syms() + n;
                 uint16_t* const soft_end = out.syms() + out.cap - 280;
@@ -738,7 +740,8 @@ private:
                 while (nxt < nchunks && (chunks_[nxt].start.kind == MarkerDecoder::NONE || chunks_[nxt].start.pos < p)) ++nxt;
                 return nxt < nchunks && chunks_[nxt].start.pos == p && chunks_[nxt].start.kind == k;
             };
-            c.status = dec.decode(c.start, stop_at, syms, &nsym, c.ends, &c.end_at, &abort_, chunk_bytes_ * 10);
+            c.status = dec.decode(c.start, stop_at, syms, &nsym, c.ends, &c.end_at, &abort_, chunk_bytes_ * 10,
+                                  std::max<size_t>(64u << 20, chunk_bytes_ * 128));
             if (c.status == MarkerDecoder::FAILED || c.status == MarkerDecoder::GARBAGE) c.err = dec.error();
         } else {
             c.status = MarkerDecoder::ABORTED;

@@ -409,6 +409,22 @@ def test_parallel_inflate_rejects_damaged_streams(tmp_path, monkeypatch):
         assert got == text, "byte %d flipped: accepted with different content" % i
 
 
+def test_parallel_inflate_hands_over_when_a_chunk_expands_too_much(tmp_path, monkeypatch):
+    """A constant matrix compresses ~500-fold: a chunk of the parallel decoder would hold hundreds of megabytes of symbols.
+    Single-member files are recognised up front (ISIZE against the file size) and stay with the sequential decoder; behind a
+    second member the size is not visible, the chunk hits its budget and zlib finishes the file.  Same text either way."""
+    row = b"chr1\t0\t200\t" + b"\t".join([b"18"] * 833) + b"\n"
+    data = row * 56000                                               # 140 MB of text in ~270 KB
+    tail = b"chr1\t0\t200\t1\t2\n" * 1000
+    monkeypatch.setenv("EPI_INFLATE_CHUNK", "200000")
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "3")
+    p = tmp_path / "const.gz"
+    p.write_bytes(gzip.compress(data, 6))
+    assert _inflate(p, monkeypatch) == data and _reader_stats()[0] == 1          # never started
+    p.write_bytes(gzip.compress(data, 6) + gzip.compress(tail, 6))
+    assert _inflate(p, monkeypatch) == data + tail and _reader_stats()[0] == 3   # started, gave up, zlib finished
+
+
 def test_parallel_and_sequential_readers_parse_the_same_matrix(tmp_path, monkeypatch):
     """read_matrix over a file large enough for the parallel decoder by default (no knobs): same labels and coordinates as
     with one inflate thread, and as the matrix that was written."""
