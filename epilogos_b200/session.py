@@ -88,14 +88,17 @@ class Shard:
             self._split, self._pinned, self._paired = split, pinned, str(file2) != "null"
             self._full = None
             if split[0] == self.reader:
-                loc, a, total = helpers.read_matrix(file1, None, want_locations=True, num_states=num_states, pinned=pinned,
-                                                    return_total=True)
-                b = None
-                if self._paired:
-                    _, b = helpers.read_matrix(file2, None, want_locations=False, num_states=num_states, pinned=pinned)
-                    if b.shape[0] != a.shape[0]:
-                        raise ValueError("paired input files must have the same number of rows")
-                self._full = (loc, a, b, total)
+                try:
+                    loc, a, total = helpers.read_matrix(file1, None, want_locations=True, num_states=num_states,
+                                                        pinned=pinned, return_total=True)
+                    b = None
+                    if self._paired:
+                        _, b = helpers.read_matrix(file2, None, want_locations=False, num_states=num_states, pinned=pinned)
+                        if b.shape[0] != a.shape[0]:
+                            raise ValueError("paired input files must have the same number of rows")
+                    self._full = (loc, a, b, total)
+                except Exception as exc:           # the other ranks wait in exchange(): tell them instead of leaving
+                    self._full = exc
             if exchange:
                 self.exchange()
             return
@@ -119,9 +122,17 @@ class Shard:
         rank, world = self._split
         meta = [None]
         if rank == self.reader:
-            loc, a, b, total = self._full
-            meta = [(int(total), int(a.shape[1]), int(b.shape[1]) if b is not None else -1)]
+            if isinstance(self._full, Exception):
+                meta = [("error", type(self._full).__name__, str(self._full))]
+            else:
+                loc, a, b, total = self._full
+                meta = [(int(total), int(a.shape[1]), int(b.shape[1]) if b is not None else -1)]
         td.broadcast_object_list(meta, src=self.reader)
+        if meta[0][0] == "error":                  # every rank fails the same way, as when each read the file itself
+            if rank == self.reader:
+                raise self._full
+            kinds = {"ValueError": ValueError, "FileNotFoundError": FileNotFoundError}
+            raise kinds.get(meta[0][1], RuntimeError)("rank %d could not read the input: %s" % (self.reader, meta[0][2]))
         total, cols_a, cols_b = meta[0]
         ranges = helpers.splitRows(total, world)
         self.total_rows = total

@@ -306,6 +306,37 @@ def test_run_stages_world_size_two_files_or_rows(tmp_path, golden, shard):
     assert len((out / "regionsOfInterest_in_s2.txt").read_text().splitlines()) > 10
 
 
+BAD_INPUT_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import torch.distributed as td
+from fake_backend import OracleBackend
+from epilogos_b200 import session
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+try:
+    session.load_shard({f!r}, "null", 18, OracleBackend())
+    print("NO ERROR", flush=True)
+except Exception as exc:
+    print("RAISED", td.get_rank(), type(exc).__name__, str(exc)[:200], flush=True)
+td.destroy_process_group()
+"""
+
+
+def test_unreadable_input_fails_on_every_rank_when_one_rank_reads(tmp_path):
+    """Rows mode with one reader per file: a file the reader cannot parse (label outside 1..numStates) raises on BOTH
+    ranks -- the reader tells the waiting rank instead of leaving it in the exchange."""
+    f = tmp_path / "epilogos_matrix_chr1.txt"
+    f.write_text("".join("chr1\t%d\t%d\t1\t2\t%d\n" % (i * 200, i * 200 + 200, 19 if i == 7 else 3) for i in range(20)))
+    port = 33500 + (os.getpid() % 2000)
+    code = BAD_INPUT_WORKER.format(root=str(ROOT), tests=str(ROOT / "tests"), port=port, f=str(f))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    logs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    raised = [line for log in logs for line in log.splitlines() if line.startswith("RAISED")]
+    assert len(raised) == 2 and all("row 7" in line and "outside 1..18" in line for line in raised), logs
+
+
 def test_deal_files_balances_by_size(tmp_path):
     from epilogos_b200 import run
     sizes = {"a": 900, "b": 500, "c": 400, "d": 300, "e": 100}
