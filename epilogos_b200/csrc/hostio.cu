@@ -524,9 +524,8 @@ struct LineSource {
                     c ? (parallel ? "parallel inflate" : "parallel inflate abandoned") : (native ? "sequential inflate" : "zlib"), c, f, a,
                     (unsigned long long)delivered);
             if (c)
-                fprintf(stderr, "[epi reader]   pool time: decode %.3f s, waiting for the predecessor %.3f s, resolve %.3f s, crc %.3f s\n",
-                        pinflater.us_decode.load() * 1e-6, pinflater.us_wait.load() * 1e-6, pinflater.us_resolve.load() * 1e-6,
-                        pinflater.us_crc.load() * 1e-6);
+                fprintf(stderr, "[epi reader]   pool time: decode %.3f s, waiting for the predecessor %.3f s, resolve + CRC-32 %.3f s\n",
+                        pinflater.us_decode.load() * 1e-6, pinflater.us_wait.load() * 1e-6, pinflater.us_resolve.load() * 1e-6);
         }
     }
 };

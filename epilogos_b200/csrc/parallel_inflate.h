@@ -687,7 +687,7 @@ private:
     std::string error_;
 
 public:
-    std::atomic<uint64_t> us_decode{0}, us_wait{0}, us_resolve{0}, us_crc{0};     // summed over the pool (diagnostics)
+    std::atomic<uint64_t> us_decode{0}, us_wait{0}, us_resolve{0};     // summed over the pool (diagnostics; resolve includes CRC-32)
 private:
     static uint64_t now_us() {
         return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -858,41 +858,44 @@ private:
         }
         if (c.bytes.size() < hist_ + nsym + 64) c.bytes.resize(hist_ + nsym + 64 + nsym / 16);
         uint8_t* o = reinterpret_cast<uint8_t*>(c.bytes.data()) + hist_;
+        // in blocks of 128 KiB, so that the CRC reads the text the table pass has just written while it is still in cache
         {
             const uint8_t* const t = lut.data();
-            size_t j = 0;
-            for (; j + 8 <= nsym; j += 8) {
-                const uint64_t w = (uint64_t)t[s[j]] | ((uint64_t)t[s[j + 1]] << 8) | ((uint64_t)t[s[j + 2]] << 16) |
-                                   ((uint64_t)t[s[j + 3]] << 24) | ((uint64_t)t[s[j + 4]] << 32) | ((uint64_t)t[s[j + 5]] << 40) |
-                                   ((uint64_t)t[s[j + 6]] << 48) | ((uint64_t)t[s[j + 7]] << 56);
-                memcpy(o + j, &w, 8);
+            constexpr size_t BLK = 128u << 10;
+            size_t next_end = 0;                                 // index into c.ends
+            uLong crc = crc32(0L, Z_NULL, 0);
+            for (size_t j0 = 0; j0 < nsym || next_end < c.ends.size(); j0 += BLK) {
+                const size_t j1 = j0 + BLK < nsym ? j0 + BLK : nsym;
+                size_t j = j0;
+                for (; j + 8 <= j1; j += 8) {
+                    const uint64_t w = (uint64_t)t[s[j]] | ((uint64_t)t[s[j + 1]] << 8) | ((uint64_t)t[s[j + 2]] << 16) |
+                                       ((uint64_t)t[s[j + 3]] << 24) | ((uint64_t)t[s[j + 4]] << 32) | ((uint64_t)t[s[j + 5]] << 40) |
+                                       ((uint64_t)t[s[j + 6]] << 48) | ((uint64_t)t[s[j + 7]] << 56);
+                    memcpy(o + j, &w, 8);
+                }
+                for (; j < j1; ++j) o[j] = t[s[j]];
+                // CRC of [j0, j1), cut at the member ends that fall inside (an end at j1 belongs to this block)
+                size_t at = j0;
+                while (next_end < c.ends.size() && (size_t)c.ends[next_end].off <= j1) {
+                    const size_t e = (size_t)c.ends[next_end].off;
+                    if (e > at) crc = crc32(crc, o + at, (uInt)(e - at));
+                    c.piece_crc.push_back((uint32_t)crc);
+                    crc = crc32(0L, Z_NULL, 0);
+                    at = e;
+                    ++next_end;
+                }
+                if (j1 > at) crc = crc32(crc, o + at, (uInt)(j1 - at));
+                if (j1 >= nsym && next_end >= c.ends.size()) break;
             }
-            for (; j < nsym; ++j) o[j] = t[s[j]];
+            c.piece_crc.push_back((uint32_t)crc);                // the open piece behind the last member end (may be empty)
         }
         c.n = nsym;
         t1 = now_us();
         us_resolve += t1 - t0;
-        size_t at = 0;
-        for (const MarkerDecoder::MemberEnd& me : c.ends) {
-            c.piece_crc.push_back(crc_of(o + at, (size_t)me.off - at));
-            at = (size_t)me.off;
-        }
-        c.piece_crc.push_back(crc_of(o + at, nsym - at));
-        us_crc += now_us() - t1;
         if (syms.cap > chunk_bytes_ * 40 + (1u << 22)) syms.release();      // do not keep an outlier's buffer around
         publish_done(c);
     }
 
-    static uint32_t crc_of(const uint8_t* p, size_t n) {
-        uLong c = crc32(0L, Z_NULL, 0);
-        while (n) {
-            const uInt step = (uInt)(n < (1u << 30) ? n : (1u << 30));
-            c = crc32(c, p, step);
-            p += step;
-            n -= step;
-        }
-        return (uint32_t)c;
-    }
 };
 
 }  // namespace epi
