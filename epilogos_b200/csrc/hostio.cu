@@ -308,7 +308,11 @@ struct LineSource {
             const uint64_t isize = size >= 18 ? ((uint64_t)packed[size - 4] | ((uint64_t)packed[size - 3] << 8) |
                                                  ((uint64_t)packed[size - 2] << 16) | ((uint64_t)packed[size - 1] << 24)) : 0;
             const bool dense = isize / 100 <= (uint64_t)size;
+            const auto t_s0 = std::chrono::steady_clock::now();
             if (threads >= 2 && size >= least && dense) parallel = pinflater.start(packed.data(), size, threads, chunk, HIST);
+            if (getenv("EPI_INFLATE_DEBUG") != nullptr)
+                fprintf(stderr, "[epi reader] chunk starts found in %.3f s\n",
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - t_s0).count());
         }
         blocks[0].resize(HIST + BLOCK + 64);
         blocks[1].resize(HIST + BLOCK + 64);
@@ -718,8 +722,10 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
                                   int32_t* cols_out, int32_t* n_chrom_out, int32_t* names_bytes_out) {
     EPI_REQUIRE(path != nullptr && handle_out != nullptr, "null pointer argument");
     EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
+    const double t_enter = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     LineSource src;
     EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    const double t_open = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_enter;
     std::unique_ptr<ParsedFile> pf(new ParsedFile());
     std::vector<std::pair<const char*, const char*>> lines;
     int last_id = -1;
@@ -799,7 +805,9 @@ extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** h
         tq = now_s();
         t_parse += tq - tc;
     }
-    if (dbg_t) fprintf(stderr, "[epi reader] parse loop: waiting for text %.3f s, line split + ids %.3f s, row parse %.3f s\n", t_wait, t_prep, t_parse);
+    if (dbg_t)
+        fprintf(stderr, "[epi reader] open (load, chunk starts, first text) %.3f s; parse loop: waiting for text %.3f s, line split + ids %.3f s, "
+                "row parse %.3f s\n", t_open, t_wait, t_prep, t_parse);
     EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
     size_t nb = 0;
     for (const std::string& s : pf->names) nb += s.size() + 1;

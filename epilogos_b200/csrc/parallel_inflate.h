@@ -27,6 +27,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -516,8 +517,10 @@ class ParallelInflate {
 public:
     ~ParallelInflate() { stop(); }
 
-    // Finds the chunk starts (synchronously, in parallel).  Returns false when parallel decoding is not worthwhile (fewer
-    // than a quarter of the chunks have a start: stored or fixed blocks only, one giant block, ...); nothing is running then.
+    // Cuts the file into chunks (small ones first, so that the first text is there early) and looks for the starts of the
+    // first few of them; the others are found by the pool when it gets to them.  Returns false when parallel decoding is
+    // not worthwhile (no second start among the probed chunks: stored or fixed blocks only, one giant block, ...);
+    // nothing is running then.
     bool start(const uint8_t* data, size_t size, int threads, size_t chunk_bytes, size_t hist) {
         data_ = data;
         size_ = size;
@@ -525,10 +528,23 @@ public:
         nthreads_ = threads < 1 ? 1 : threads;
         if (chunk_bytes < 1024) chunk_bytes = 1024;
         chunk_bytes_ = chunk_bytes;
-        const size_t n = (size + chunk_bytes - 1) / chunk_bytes;
+        offsets_.clear();
+        {
+            size_t at = 0, step = chunk_bytes / 8 < 1024 ? 1024 : chunk_bytes / 8;
+            while (at < size) {
+                offsets_.push_back(at);
+                at += step;
+                if (offsets_.size() % (size_t)nthreads_ == 0 && step < chunk_bytes) step = step * 2 < chunk_bytes ? step * 2 : chunk_bytes;
+            }
+            offsets_.push_back(size);
+        }
+        const size_t n = offsets_.size() - 1;
         if (n < 2) return false;
-        chunks_.resize(n);
+        nchunks_ = n;
+        chunks_.reset(new Chunk[n]);
+        links_.clear();
         links_.resize(n + 1);
+        const size_t probe = n < (size_t)nthreads_ * 2 ? n : (size_t)nthreads_ * 2;
         {
             std::atomic<size_t> next(0);
             auto finder = [&]() {
@@ -536,23 +552,19 @@ public:
                 SymbolBuffer scratch;
                 for (;;) {
                     const size_t i = next.fetch_add(1);
-                    if (i >= n) break;
-                    if (i == 0) {
-                        chunks_[0].start.pos = 0;
-                        chunks_[0].start.kind = MarkerDecoder::MEMBER;
-                    } else {
-                        chunks_[i].start = dec.find_start(i * chunk_bytes_, (i + 1) * chunk_bytes_, scratch);
-                    }
+                    if (i >= probe) break;
+                    chunk_start(i, dec, scratch);
                 }
             };
             std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads_; ++t) pool.emplace_back(finder);
+            for (int t = 0; t < nthreads_ && (size_t)t < probe; ++t) pool.emplace_back(finder);
             for (auto& th : pool) th.join();
         }
         size_t found = 0;
-        for (const Chunk& c : chunks_) found += c.start.kind != MarkerDecoder::NONE;
-        if (found * 4 < n || found < 2) {
-            chunks_.clear();
+        for (size_t i = 0; i < probe; ++i) found += chunks_[i].start.kind != MarkerDecoder::NONE;
+        if (found < 2) {
+            chunks_.reset();
+            nchunks_ = 0;
             links_.clear();
             return false;
         }
@@ -570,7 +582,7 @@ public:
     int next(std::vector<char>& bytes, size_t* n) {
         for (;;) {
             if (failed_) return -1;
-            if (consumed_ == chunks_.size()) {
+            if (consumed_ == nchunks_) {
                 if (!ended_) return set_failed("the chunk chain did not reach the end of the stream");
                 return 0;
             }
@@ -628,14 +640,14 @@ public:
     // diagnostics: chunks the file was cut into, chunks with a start, chunks accepted into the chain so far
     void stats(size_t* chunks, size_t* with_start, size_t* accepted) {
         std::lock_guard<std::mutex> lk(mu_);
-        *chunks = chunks_.size();
+        *chunks = nchunks_;
         *with_start = *accepted = 0;
-        for (const Chunk& c : chunks_) {
-            *with_start += c.start.kind != MarkerDecoder::NONE;
+        for (size_t i = 0; i < nchunks_; ++i) {
+            const Chunk& c = chunks_[i];
+            *with_start += c.start_known.load() == 2 && c.start.kind != MarkerDecoder::NONE;
             *accepted += c.done && !c.discarded && c.status <= MarkerDecoder::END_OF_STREAM;
         }
     }
-
     // may be called from several threads (the reader's worker on a failure, the reader's owner on destruction)
     void stop() {
         std::lock_guard<std::mutex> guard(stop_mu_);
@@ -652,6 +664,8 @@ public:
 private:
     struct Chunk {
         MarkerDecoder::Start start, end_at;
+        std::atomic<int> start_known{0};          // 2 once `start` holds the finder's answer
+        std::mutex start_mu;
         int status = MarkerDecoder::FAILED;
         std::vector<MarkerDecoder::MemberEnd> ends;
         std::vector<uint32_t> piece_crc;          // one per piece between member ends (the last one may be open)
@@ -672,7 +686,9 @@ private:
     const uint8_t* data_ = nullptr;
     size_t size_ = 0, hist_ = 0, chunk_bytes_ = 0, max_inflight_ = 4;
     int nthreads_ = 1;
-    std::vector<Chunk> chunks_;
+    std::unique_ptr<Chunk[]> chunks_;             // not movable (mutex): a plain array
+    size_t nchunks_ = 0;
+    std::vector<size_t> offsets_;                 // chunk i covers bytes [offsets_[i], offsets_[i + 1])
     std::vector<Link> links_;
     std::vector<std::thread> pool_;
     std::vector<std::vector<char>> spare_;        // text buffers handed back by next(), guarded by mu_
@@ -698,10 +714,28 @@ private:
         return -1;
     }
 
+    // The start of chunk i, found on first use by whoever needs it first (the chunk's own worker, or the worker of an
+    // earlier chunk that has to know where to stop).  `finder` must not be the decoder that is in the middle of a chunk.
+    const MarkerDecoder::Start& chunk_start(size_t i, MarkerDecoder& finder, SymbolBuffer& scratch) {
+        Chunk& c = chunks_[i];
+        if (c.start_known.load(std::memory_order_acquire) == 2) return c.start;
+        std::lock_guard<std::mutex> lk(c.start_mu);
+        if (c.start_known.load(std::memory_order_relaxed) != 2) {
+            if (i == 0) {
+                c.start.pos = 0;
+                c.start.kind = MarkerDecoder::MEMBER;
+            } else {
+                c.start = finder.find_start(offsets_[i], offsets_[i + 1], scratch);
+            }
+            c.start_known.store(2, std::memory_order_release);
+        }
+        return c.start;
+    }
+
     void worker() {
-        MarkerDecoder dec(data_, size_);
-        SymbolBuffer syms;
-        const size_t n = chunks_.size();
+        MarkerDecoder dec(data_, size_), finder(data_, size_);
+        SymbolBuffer syms, scratch;
+        const size_t n = nchunks_;
         for (;;) {
             size_t i;
             {
@@ -710,7 +744,7 @@ private:
                 i = next_chunk_++;
                 cv_.wait(lk, [&] { return i < consumed_ + max_inflight_ || abort_.load(); });
             }
-            process(i, dec, syms);
+            process(i, dec, finder, syms, scratch);
         }
     }
 
@@ -729,16 +763,21 @@ private:
         cv_.notify_all();
     }
 
-    void process(size_t i, MarkerDecoder& dec, SymbolBuffer& syms) {
+    void process(size_t i, MarkerDecoder& dec, MarkerDecoder& finder, SymbolBuffer& syms, SymbolBuffer& scratch) {
         Chunk& c = chunks_[i];
-        const size_t nchunks = chunks_.size();
+        const size_t nchunks = nchunks_;
         size_t nsym = 0;
         uint64_t t0 = now_us();
-        if (c.start.kind != MarkerDecoder::NONE && !abort_.load()) {
+        if (!abort_.load()) chunk_start(i, finder, scratch);
+        if (c.start_known.load() == 2 && c.start.kind != MarkerDecoder::NONE && !abort_.load()) {
             size_t nxt = i + 1;
             auto stop_at = [&](uint64_t p, MarkerDecoder::Kind k) {
-                while (nxt < nchunks && (chunks_[nxt].start.kind == MarkerDecoder::NONE || chunks_[nxt].start.pos < p)) ++nxt;
-                return nxt < nchunks && chunks_[nxt].start.pos == p && chunks_[nxt].start.kind == k;
+                while (nxt < nchunks) {
+                    const MarkerDecoder::Start& st = chunk_start(nxt, finder, scratch);
+                    if (st.kind != MarkerDecoder::NONE && st.pos >= p) return st.pos == p && st.kind == k;
+                    ++nxt;
+                }
+                return false;
             };
             c.status = dec.decode(c.start, stop_at, syms, &nsym, c.ends, &c.end_at, &abort_, chunk_bytes_ * 10,
                                   std::max<size_t>(64u << 20, chunk_bytes_ * 128));

@@ -332,11 +332,12 @@ def test_parallel_inflate_equals_the_data_for_every_stream_shape(tmp_path, monke
                 assert st[0] in (1, 2), (name, tag, chunk, threads, st)          # never the zlib fall-back on valid input
                 taken[(name, tag, chunk)] = st
             p.unlink()
-    # dynamic-Huffman streams cut into chunks of a few blocks: every chunk has a start and every chunk is accepted
+    # dynamic-Huffman streams cut into chunks of a few blocks (the first chunks are smaller): most chunks have a start
+    # and every start that was found is accepted
     for name in ("matrix", "lowentropy", "mixed"):
         for tag in ("l6", "l9", "members3", "bgzf"):
             st = taken[(name, tag, 150000)]
-            assert st[0] == 2 and st[1] >= 2 and st[3] >= st[1] - 1, (name, tag, st)
+            assert st[0] == 2 and st[2] >= 3 and st[2] * 2 >= st[1] and st[3] == st[2], (name, tag, st)
     assert taken[("matrix", "fixed", 20000)][0] == 1                             # fixed blocks only: nothing to start from
     monkeypatch.setenv("EPI_INFLATE_THREADS", "1")                               # one thread: the sequential decoder
     p = tmp_path / "seq.gz"
@@ -416,8 +417,8 @@ def test_parallel_inflate_hands_over_when_a_chunk_expands_too_much(tmp_path, mon
     row = b"chr1\t0\t200\t" + b"\t".join([b"18"] * 833) + b"\n"
     data = row * 56000                                               # 140 MB of text in ~270 KB
     tail = b"chr1\t0\t200\t1\t2\n" * 1000
-    monkeypatch.setenv("EPI_INFLATE_CHUNK", "200000")
-    monkeypatch.setenv("EPI_INFLATE_THREADS", "3")
+    monkeypatch.setenv("EPI_INFLATE_CHUNK", "500000")               # chunks of 62.5, 62.5 and 125 KB: the third expands to 69 MB
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "2")
     p = tmp_path / "const.gz"
     p.write_bytes(gzip.compress(data, 6))
     assert _inflate(p, monkeypatch) == data and _reader_stats()[0] == 1          # never started
