@@ -20,14 +20,16 @@ FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=s
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu"))
+    """CUDA sources and the plain C++ ones (host code that wants the host compiler alone, e.g. SIMD intrinsics behind a
+    target attribute); nvcc hands a .cpp straight to g++."""
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
 def _stale():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "epilogos_b200.h",
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "epilogos_b200.h",
                                                                   Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 

@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "fast_inflate.h"
+#include "label_simd.h"
 #include "parallel_inflate.h"
 
 namespace epi {
@@ -62,7 +63,9 @@ static int inflate_threads() {
         const int v = atoi(e);
         if (v >= 1) return v > 32 ? 32 : v;
     }
-    const int t = std::min(8, cores_per_reader() / 2);
+    // three quarters of the reader's cores: decoding, marker resolution and CRC take ~3 ns per byte of text, the SIMD row
+    // parser ~1 ns (measured)
+    const int t = std::min(12, (cores_per_reader() * 3 + 2) / 4);
     return t < 2 ? 1 : t;
 }
 
@@ -574,6 +577,16 @@ static int parse_row(const char* path, int64_t row, const char* p, const char* e
     }
     // ---- state labels: 1..num_states, one to three digits ----
     int j = 0;
+    // wide rows: 16 bytes at a time (label_simd.cpp) up to the last few labels; anything but one- and two-digit labels in
+    // range makes it step back (-1) and the scalar loops below parse the row from here and report what is wrong
+    if (cols >= 48 && label_simd_available() && getenv("EPI_PARSE_SCALAR") == nullptr) {      // (the knob: for A/B runs and tests)
+        const char* resume = p;
+        const int got = parse_labels_simd(p, e, cols - 1, num_states, dst, &resume);
+        if (got > 0) {
+            j = got;
+            p = resume;
+        }
+    }
     // fast path for all but the last column: a one- or two-digit label and its tab, three comparisons per label.  Anything
     // else (three digits, a bad character, a label out of range, a short row) falls through to the careful loop below,
     // which parses it again from the same position and reports what is wrong.
@@ -715,7 +728,7 @@ static int parse_threads() {
         const int v = atoi(e);
         if (v >= 1) return v > 16 ? 16 : v;
     }
-    return std::max(1, std::min(8, epi::cores_per_reader() / 2));
+    return std::max(1, std::min(8, (epi::cores_per_reader() + 2) / 3));
 }
 
 extern "C" int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out,

@@ -239,6 +239,76 @@ def test_parser_fast_and_careful_paths_agree(tmp_path):
             helpers.read_matrix(p, num_states=18)
 
 
+def test_simd_and_scalar_row_parsers_agree(tmp_path, monkeypatch):
+    """The 16-bytes-at-a-time label tokenizer (csrc/label_simd.cpp, rows of at least 48 columns) against the scalar loops
+    (EPI_PARSE_SCALAR=1): same labels for every mix of one-, two- and three-digit labels and every row width around the
+    window and tail boundaries, and the same error -- row, column and reason -- for every kind of damaged row."""
+    rng = np.random.default_rng(21)
+
+    def both(path, k):
+        monkeypatch.delenv("EPI_PARSE_SCALAR", raising=False)
+        try:
+            a = helpers.read_matrix(path, num_states=k)[1].copy()
+        except EpilogosB200Error as exc:
+            a = str(exc)
+        monkeypatch.setenv("EPI_PARSE_SCALAR", "1")
+        try:
+            b = helpers.read_matrix(path, num_states=k)[1].copy()
+        except EpilogosB200Error as exc:
+            b = str(exc)
+        monkeypatch.delenv("EPI_PARSE_SCALAR", raising=False)
+        return a, b
+
+    for cols in (47, 48, 49, 63, 64, 65, 66, 79, 80, 81, 100, 127, 300, 833):
+        for k in (5, 9, 10, 18, 99, 100, 127):
+            x = rng.integers(1, k + 1, (40, cols))
+            x[rng.random(x.shape) < 0.5] = k
+            p = tmp_path / "m.txt"
+            p.write_text("".join("chr%d\t%d\t%d\t%s\n" % (i % 3, i * 200, i * 200 + 200, "\t".join(map(str, r)))
+                                 for i, r in enumerate(x.tolist())))
+            a, b = both(p, k)
+            assert isinstance(a, np.ndarray) and np.array_equal(a, x - 1) and np.array_equal(b, x - 1), (cols, k)
+    p.write_text("".join("chr1\t%d\t%d\t%s\r\n" % (i * 200, i * 200 + 200, "\t".join(map(str, r))) for i, r in enumerate(x.tolist())))
+    a, b = both(p, 127)                                              # CRLF line ends
+    assert np.array_equal(a, x - 1) and np.array_equal(b, x - 1)
+    # damaged rows: whatever the tokenizer meets, the error is the scalar parser's
+    x = rng.integers(1, 19, (30, 200))
+    rows = ["chr1\t%d\t%d\t%s" % (i * 200, i * 200 + 200, "\t".join(map(str, r))) for i, r in enumerate(x.tolist())]
+    for trial in range(160):
+        broken = list(rows)
+        r = int(rng.integers(0, len(rows)))
+        f = broken[r].split("\t")
+        c = 3 + int(rng.integers(0, 200))
+        kind = trial % 8
+        if kind == 0:
+            f[c] = "19"
+        elif kind == 1:
+            f[c] = "0"
+        elif kind == 2:
+            f[c] = ""
+        elif kind == 3:
+            f[c] = "1x"
+        elif kind == 4:
+            f[c] = "-3"
+        elif kind == 5:
+            f[c] = "007"
+        elif kind == 6:
+            f = f[:c] + f[c + 1:]                                    # a column short
+        else:
+            f = f[:c] + ["7"] + f[c:]                                # a column too many
+        broken[r] = "\t".join(f)
+        p.write_text("\n".join(broken) + "\n")
+        a, b = both(p, 18)
+        if kind == 5:                                                # leading zeros are an integer all the same (as for pandas)
+            want = x - 1
+            want[r, c - 3] = 6
+            assert isinstance(a, np.ndarray) and np.array_equal(a, want) and np.array_equal(b, want), trial
+            continue
+        # (the column count is taken from the first row: a first row with a column more or less shifts the blame to row 1)
+        blamed = 1 if (r == 0 and kind in (6, 7)) else r
+        assert isinstance(a, str) and a == b and ("row %d" % blamed) in a, (trial, kind, a, b)
+
+
 def test_native_inflate_reads_the_writers_multi_member_files_across_blocks(tmp_path, monkeypatch):
     """What the score writer emits (one gzip member per 16384 rows) read back by the native decoder: dozens of member
     boundaries, some of them inside a 16 MB reader block, CRC-32 / length checked for each; and the score reader on top."""
