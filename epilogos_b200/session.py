@@ -60,12 +60,19 @@ def _pack_locations(loc):
 
 
 def _unpack_locations(packed):
-    chrom = np.empty(sum(packed["runs"]), dtype=object)
+    n = sum(packed["runs"])
+    chrom = np.empty(n, dtype=object)
+    table = []                                     # distinct names in order of first appearance, as the native parser lists them
+    cid = np.empty(n, dtype=np.int32)
     at = 0
     for name, run in zip(packed["names"], packed["runs"]):
+        if name not in table:
+            table.append(name)
         chrom[at:at + run] = name
+        cid[at:at + run] = table.index(name)
         at += run
-    return dict(chrom=chrom, start=packed["start"], end=packed["end"])
+    return dict(chrom=chrom, start=packed["start"], end=packed["end"], chrom_id=cid,
+                chrom_names=b"".join(t.encode() + b"\0" for t in table) or b"\0")
 
 
 class Shard:
@@ -150,7 +157,7 @@ class Shard:
         self.loc = None
         if self.reader == 0:
             if rank == 0:
-                self.loc_full = {k: loc[k] for k in ("chrom", "start", "end")}
+                self.loc_full = loc                # with the parser's chromosome ids: the writer needs no np.unique
         else:
             box = [_pack_locations(loc)] if rank == self.reader else [None]
             if rank == self.reader:
