@@ -788,15 +788,17 @@ private:
         // ---- the chain: wait for the predecessor's link
         uint64_t t1 = now_us();
         us_decode += t1 - t0;
+        bool have_link;
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return links_[i].ready || abort_.load(); });
+            have_link = links_[i].ready;
         }
         t0 = now_us();
         us_wait += t0 - t1;
         Link& in = links_[i];
         Link& out = links_[i + 1];
-        if (abort_.load() && !in.ready) {
+        if (!have_link) {                        // woken by stop(): the predecessor never got here
             c.status = MarkerDecoder::ABORTED;
             c.err = "aborted";
             out.failed = true;
