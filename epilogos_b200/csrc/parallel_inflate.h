@@ -130,6 +130,23 @@ public:
                 const uint32_t v = (uint32_t)(w >> k);
                 if ((v & 7u) != 4u) continue;                               // BFINAL = 0, BTYPE = 2 (dynamic)
                 if (((v >> 3) & 31u) > 29u || ((v >> 8) & 31u) > 29u) continue;   // HLIT <= 286, HDIST <= 30
+                {
+                    // the code-length code right behind (HCLEN x 3 bits from bit 17) must be a complete prefix code: the
+                    // Kraft sum over its first 18 lengths settles that for all but one candidate in thousands, from the
+                    // bits at hand (the full header parse of plausible_block costs ~150 ns)
+                    const unsigned hclen = ((v >> 13) & 15u) + 4u;
+                    uint64_t w2;
+                    memcpy(&w2, q + 2, 8);
+                    uint64_t cl = w2 >> (k + 1);                          // bit 17 of the candidate onwards, >= 56 bits
+                    const unsigned m = hclen < 18u ? hclen : 18u;
+                    unsigned sum = 0;
+                    for (unsigned i = 0; i < m; ++i) {
+                        const unsigned len = (unsigned)(cl & 7u);
+                        cl >>= 3;
+                        sum += len ? (128u >> len) : 0u;
+                    }
+                    if (sum > 128u || (hclen <= 18u && sum != 128u)) continue;
+                }
                 if (plausible_block((uint64_t)b * 8 + (uint64_t)k, scratch)) {
                     Start s;
                     s.pos = (uint64_t)b * 8 + (uint64_t)k;
