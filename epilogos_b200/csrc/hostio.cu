@@ -242,7 +242,7 @@ struct LineSource {
             if (inflater.at_end_of_input()) break;
             uint8_t* np = out;
             const FastInflate::Status st = inflater.decode(out, end, &np);
-            crc = (uint32_t)crc32(crc, out, (uInt)(np - out));
+            crc = crc32_fast(crc, out, (size_t)(np - out));
             member_bytes += (uint64_t)(np - out);
             const bool produced = np != out;
             out = np;

@@ -33,6 +33,7 @@
 #include <thread>
 #include <vector>
 
+#include "crc_clmul.h"
 #include "fast_inflate.h"
 
 namespace epi {
@@ -921,7 +922,7 @@ private:
             const uint8_t* const t = lut.data();
             constexpr size_t BLK = 128u << 10;
             size_t next_end = 0;                                 // index into c.ends
-            uLong crc = crc32(0L, Z_NULL, 0);
+            uint32_t crc = 0;                                    // = crc32(0, NULL, 0)
             for (size_t j0 = 0; j0 < nsym || next_end < c.ends.size(); j0 += BLK) {
                 const size_t j1 = j0 + BLK < nsym ? j0 + BLK : nsym;
                 size_t j = j0;
@@ -936,16 +937,16 @@ private:
                 size_t at = j0;
                 while (next_end < c.ends.size() && (size_t)c.ends[next_end].off <= j1) {
                     const size_t e = (size_t)c.ends[next_end].off;
-                    if (e > at) crc = crc32(crc, o + at, (uInt)(e - at));
-                    c.piece_crc.push_back((uint32_t)crc);
-                    crc = crc32(0L, Z_NULL, 0);
+                    if (e > at) crc = crc32_fast(crc, o + at, e - at);
+                    c.piece_crc.push_back(crc);
+                    crc = 0;
                     at = e;
                     ++next_end;
                 }
-                if (j1 > at) crc = crc32(crc, o + at, (uInt)(j1 - at));
+                if (j1 > at) crc = crc32_fast(crc, o + at, j1 - at);
                 if (j1 >= nsym && next_end >= c.ends.size()) break;
             }
-            c.piece_crc.push_back((uint32_t)crc);                // the open piece behind the last member end (may be empty)
+            c.piece_crc.push_back(crc);                          // the open piece behind the last member end (may be empty)
         }
         c.n = nsym;
         t1 = now_us();

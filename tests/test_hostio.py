@@ -239,6 +239,32 @@ def test_parser_fast_and_careful_paths_agree(tmp_path):
             helpers.read_matrix(p, num_states=18)
 
 
+def test_gzip_trailer_crc_is_checked_by_both_crc_paths(tmp_path, monkeypatch):
+    """The CRC-32 of the trailer check runs on carry-less multiplies where the CPU has them (csrc/crc_clmul.cpp) and on zlib's
+    tables otherwise and for short pieces: members of every length around the 64-byte folding width and the 256-byte
+    switch-over decode, and a flipped CRC byte is still caught -- sequential and parallel decoder."""
+    rng = np.random.default_rng(31)
+    data = rng.integers(32, 127, 3_000_000, dtype=np.uint8).tobytes()
+    sizes = [0, 1, 15, 16, 17, 63, 64, 65, 127, 128, 255, 256, 257, 319, 320, 1000, 4095, 65536, 65537, 700001]
+    blob, at = b"", 0
+    for n in sizes:
+        blob += gzip.compress(data[at:at + n], 6)
+        at += n
+    p = tmp_path / "members.gz"
+    p.write_bytes(blob)
+    for threads, chunk in ((1, None), (3, 60000)):
+        monkeypatch.setenv("EPI_INFLATE_THREADS", str(threads))
+        if chunk:
+            monkeypatch.setenv("EPI_INFLATE_CHUNK", str(chunk))
+        assert _inflate(p, monkeypatch) == data[:at]
+        bad = bytearray(blob)
+        bad[-6] ^= 0x20                                              # CRC-32 field of the last (700,001-byte) member
+        p.write_bytes(bytes(bad))
+        with pytest.raises(EpilogosB200Error):
+            _inflate(p, monkeypatch)
+        p.write_bytes(blob)
+
+
 def test_simd_and_scalar_row_parsers_agree(tmp_path, monkeypatch):
     """The 16-bytes-at-a-time label tokenizer (csrc/label_simd.cpp, rows of at least 48 columns) against the scalar loops
     (EPI_PARSE_SCALAR=1): same labels for every mix of one-, two- and three-digit labels and every row width around the
