@@ -288,9 +288,18 @@ private:
         return true;
     }
 
-    static inline void copy_match(uint8_t* dst, uint32_t dist, uint32_t len) {
-        // dst - dist .. may overlap dst; may write up to 8 bytes past dst + len (the caller leaves that slack)
+    static inline void copy_match(uint8_t* dst, uint32_t dist, uint32_t len, bool wide) {
+        // dst - dist .. may overlap dst; may write up to 8 bytes (wide: 32) past dst + len (the caller leaves that slack)
         const uint8_t* src = dst - dist;
+        if (dist >= 32 && wide) {                               // 32 bytes per step (label matrices copy whole rows: long matches)
+            uint8_t* end = dst + len;
+            do {
+                memcpy(dst, src, 32);
+                src += 32;
+                dst += 32;
+            } while (dst < end);
+            return;
+        }
         if (dist >= 8) {
             uint8_t* end = dst + len;
             do {
@@ -472,7 +481,7 @@ private:
                 }
                 const size_t room = (size_t)(out_end - out);
                 if (len + 8 <= room) {
-                    copy_match(out, dist, len);
+                    copy_match(out, dist, len, len + 32 <= room);
                     out += len;
                 } else {
                     const uint32_t n = len < room ? len : (uint32_t)room;
