@@ -144,15 +144,22 @@ class Shard:
         ranges = helpers.splitRows(total, world)
         self.total_rows = total
         self.lo, self.hi = ranges[rank]
-        full_a = full_b = None
-        if rank == self.reader:
-            full_a = a.base if isinstance(a.base, np.ndarray) and a.base.shape[0] == a.shape[0] else np.ascontiguousarray(a)
-            if b is not None:
-                full_b = b.base if isinstance(b.base, np.ndarray) and b.base.shape[0] == b.shape[0] else np.ascontiguousarray(b)
-        self.states_a = dist.deal_rows(full_a, ranges, self.reader, helpers.pitch_for(max(cols_a, 1)), self._pinned)[:, :cols_a]
+        def pitched(m, pitch):
+            """The [rows, pitch] buffer behind a matrix of read_matrix (it is a view of one), else a pitched copy."""
+            base = m.base
+            if (isinstance(base, np.ndarray) and base.dtype == np.int8 and base.ndim == 2 and base.flags.c_contiguous
+                    and base.shape == (m.shape[0], pitch) and (m.size == 0 or m.ctypes.data == base.ctypes.data)):
+                return base
+            out = np.zeros((m.shape[0], pitch), dtype=np.int8)
+            out[:, :m.shape[1]] = m
+            return out
+        pitch_a, pitch_b = helpers.pitch_for(max(cols_a, 1)), helpers.pitch_for(max(cols_b, 1))
+        full_a = pitched(a, pitch_a) if rank == self.reader else None
+        full_b = pitched(b, pitch_b) if rank == self.reader and b is not None else None
+        self.states_a = dist.deal_rows(full_a, ranges, self.reader, pitch_a, self._pinned)[:, :cols_a]
         self.states_b = None
         if cols_b >= 0:
-            self.states_b = dist.deal_rows(full_b, ranges, self.reader, helpers.pitch_for(max(cols_b, 1)), self._pinned)[:, :cols_b]
+            self.states_b = dist.deal_rows(full_b, ranges, self.reader, pitch_b, self._pinned)[:, :cols_b]
         # locations: only the writing rank needs them
         self.loc = None
         if self.reader == 0:
