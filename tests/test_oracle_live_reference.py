@@ -12,7 +12,8 @@ import pytest
 from oracle import epilogos_oracle as orc
 from oracle import reference_driver as ref
 
-pytestmark = pytest.mark.skipif(not ref.available(), reason="the reference is neither at /root/reference nor staged in oracle/_ref")
+pytestmark = [pytest.mark.skipif(not ref.available(), reason="the reference is neither at /root/reference nor staged in oracle/_ref"),
+              pytest.mark.filterwarnings("ignore:This process .* is multi-threaded, use of fork:DeprecationWarning")]   # its Pool
 
 
 def _matrix(rng, bins, cols, k, kind):
