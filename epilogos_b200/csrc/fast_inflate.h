@@ -10,7 +10,8 @@
 // resumed by the next call) and reports the end of every gzip member so that the caller can check CRC-32 and ISIZE.
 // Every malformed input is an error return, never undefined behaviour: table construction rejects over-subscribed
 // codes, unassigned codes decode to an error entry, distances are checked against the bytes produced so far, and the
-// input pointer may overrun only into the 16 zero bytes the caller appends.
+// input pointer may overrun only into the zero bytes the caller appends (a refill reads 8 bytes ahead and a block header
+// takes a few refills between its checks: 16 bytes are the minimum, the reader appends 64).
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -24,7 +25,7 @@ class FastInflate {
 public:
     enum Status { OUT_FULL = 0, MEMBER_END = 1, ERROR = 2 };
 
-    // [data, data + size) must be followed by at least 16 readable bytes (zeros)
+    // [data, data + size) must be followed by zero bytes (see above)
     void reset(const uint8_t* data, size_t size) {
         in_ = data;
         in_end_ = data + size;

@@ -189,6 +189,7 @@ extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_
 struct LineSource {
     static constexpr size_t BLOCK = 16u << 20;
     static constexpr size_t HIST = 32768;       // DEFLATE window kept in front of every block for the native decoder
+    static constexpr size_t PACK_PAD = 64;      // zero bytes behind the compressed file: the decoders' bit readers run ahead
     gzFile gz = nullptr;
     std::vector<char> blocks[2];                // [HIST bytes of history | BLOCK bytes of text | slack]
     size_t lens[2] = {0, 0};
@@ -223,7 +224,7 @@ struct LineSource {
         if (gzip && fseek(f, 0, SEEK_END) == 0) {
             const long long size = ftell(f);
             if (size > 0 && fseek(f, 0, SEEK_SET) == 0) {
-                packed.assign((size_t)size + 16, 0);
+                packed.assign((size_t)size + PACK_PAD, 0);
                 ok = fread(packed.data(), 1, (size_t)size, f) == (size_t)size;
             }
         }
@@ -294,9 +295,9 @@ struct LineSource {
             if (!gz) return false;
             gzbuffer(gz, 1 << 20);
         } else {
-            inflater.reset(packed.data(), packed.size() - 16);
+            inflater.reset(packed.data(), packed.size() - PACK_PAD);
             // large single files: decode the one stream with several threads
-            const size_t size = packed.size() - 16;
+            const size_t size = packed.size() - PACK_PAD;
             const int threads = inflate_threads();
             size_t chunk = std::min<size_t>(1u << 20, std::max<size_t>(256u << 10, size / (size_t)(8 * std::max(1, threads))));
             size_t least = 2u << 20;

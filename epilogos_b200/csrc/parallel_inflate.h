@@ -81,7 +81,8 @@ public:
         uint32_t crc, isize;
     };
 
-    // [data, data + size) must be followed by at least 16 readable zero bytes
+    // [data, data + size) must be followed by readable zero bytes (the reader appends 64: a refill reads 8 bytes ahead and a
+    // block header takes a few refills between its checks)
     MarkerDecoder(const uint8_t* data, size_t size) : base_(data), end_(data + size), lim_(data + size + 8) {}
     const char* error() const { return err_; }
 
