@@ -898,6 +898,7 @@ private:
         out.kind = c.end_at.kind;
         out.ended = c.status == MarkerDecoder::END_OF_STREAM;
         publish_link(i + 1);
+        std::vector<uint8_t>().swap(in.window);              // only this chunk read it (the table holds a copy): 32 KiB per chunk add up
         if (const char* dbg = getenv("EPI_INFLATE_DEBUG"); dbg != nullptr && dbg[0] == '2') {
             size_t marks = 0, last = 0;
             for (size_t j = 0; j < nsym; ++j)
