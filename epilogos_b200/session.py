@@ -36,9 +36,18 @@ def get_backend(backend=None):
 
 def one_reader():
     """With the rows of a file sharded over several ranks, ONE rank reads the file and deals the row ranges to the others
-    (default), instead of every rank inflating and parsing the whole file to keep its 1/N of the rows
-    (EPILOGOS_B200_READ=redundant: the behaviour up to round 2, no exchange of rows)."""
-    return os.environ.get("EPILOGOS_B200_READ", "deal") != "redundant"
+    (EPILOGOS_B200_READ=deal), instead of every rank inflating and parsing the whole file to keep its 1/N of the rows
+    (EPILOGOS_B200_READ=redundant: the behaviour up to round 2, no exchange of rows).  Unset: deal over gloo, where the
+    exchange is covered by the CPU suite; over NCCL the exchange (device tensors, point-to-point) was written without a GPU
+    at hand, so it stays opt-in until tools/mgpu_check.py has passed with it on a multi-GPU box."""
+    mode = os.environ.get("EPILOGOS_B200_READ", "")
+    if mode in ("deal", "redundant"):
+        return mode == "deal"
+    try:
+        import torch.distributed as td
+        return td.is_available() and td.is_initialized() and td.get_backend() == "gloo"
+    except Exception:
+        return False
 
 
 def reader_of(file1, world):

@@ -804,7 +804,7 @@ def test_two_gpu_stage_drivers_match_goldens(eng):
     import os
     root = Path(__file__).resolve().parent.parent
     # rows of every file over the ranks, read by every rank itself (the path measured in round 2) and dealt by one reader
-    # rank per file (the default since; its NCCL branch was written without a GPU at hand)
+    # rank per file (opt-in over NCCL until this test has passed on hardware: its NCCL branch was written without a GPU)
     for port, mode in ((29577, "redundant"), (29578, "deal")):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                             "--master-addr", "127.0.0.1", "--master-port", str(port), str(root / "tools" / "mgpu_check.py")],
