@@ -1113,3 +1113,148 @@ extern "C" int epi_write_scores_gz(const char* path, const char* chrom_names, co
     EPI_REQUIRE(ok, "short write to %s", path);
     return 0;
 }
+
+// ---- ChromHMM `-printstatebyline` files -> matrix: the native form of bin/preprocess_data_ChromHMM.sh.
+//      One file per biosample and chromosome: line 1 `<biosample> <chr>`, line 2 `MaxState E`, then one state label per 200 bp
+//      bin.  The script pastes the files of a chromosome side by side and prefixes every row with `chr, start, end`
+//      (preprocess_data_ChromHMM.sh:34-49).  epi_statebyline_read parses ONE file straight into a column of the int8 matrix
+//      (no text matrix in between); epi_write_matrix_tsv writes the script's text for callers that want the file. ----------
+extern "C" int epi_statebyline_read(const char* path, int8_t* out, int64_t stride, int64_t cap_rows, int32_t num_states,
+                                    int64_t* rows_out, char* chrom_out, int32_t chrom_cap) {
+    EPI_REQUIRE(path != nullptr && rows_out != nullptr, "null pointer argument");
+    EPI_REQUIRE(out == nullptr || stride >= 1, "bad stride");
+    EPI_REQUIRE(num_states >= 1 && num_states <= 127, "num_states=%d out of range", num_states);
+    LineSource src;
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    const char *p, *e;
+    bool has_nl;
+    int64_t line = 0, rows = 0;
+    while (src.next_line(p, e, has_nl)) {
+        if (e > p && e[-1] == '\r') --e;
+        ++line;
+        if (line == 1) {
+            // `<biosample> <chr>`: the chromosome is the second whitespace-separated field (awk's $2 of the pasted line)
+            const char* q = p;
+            while (q < e && *q != '\t' && *q != ' ') ++q;
+            while (q < e && (*q == '\t' || *q == ' ')) ++q;
+            const char* c0 = q;
+            while (q < e && *q != '\t' && *q != ' ') ++q;
+            EPI_REQUIRE(q > c0, "%s: the first line does not name a chromosome (`<biosample> <chr>` expected)", path);
+            if (chrom_out != nullptr) {
+                EPI_REQUIRE((int64_t)(q - c0) + 1 <= (int64_t)chrom_cap, "chromosome name buffer too small");
+                memcpy(chrom_out, c0, (size_t)(q - c0));
+                chrom_out[q - c0] = 0;
+            }
+            continue;
+        }
+        if (line == 2) continue;                                   // `MaxState E`
+        if (p == e && !has_nl) break;
+        unsigned v = 0;
+        const char* q = p;
+        EPI_REQUIRE(q < e, "%s: line %lld is empty (a state label expected)", path, (long long)line);
+        while (q < e && (unsigned)(*q - '0') <= 9 && v <= 1000) v = v * 10 + (unsigned)(*q++ - '0');
+        EPI_REQUIRE(q == e, "%s: line %lld: state label is not an integer", path, (long long)line);
+        EPI_REQUIRE(v >= 1 && v <= (unsigned)num_states, "%s: line %lld: state %u outside 1..%d", path, (long long)line, v, num_states);
+        if (out != nullptr) {
+            EPI_REQUIRE(rows < cap_rows, "%s has more than %lld bins", path, (long long)cap_rows);
+            out[rows * stride] = (int8_t)(v - 1);
+        }
+        ++rows;
+    }
+    EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
+    EPI_REQUIRE(line >= 2, "%s: two header lines expected", path);
+    *rows_out = rows;
+    return 0;
+}
+
+// `chrom \t start \t end \t label_1 .. label_C` per bin, start = (first_bin + r) * bin_size, labels 1-based: the text of the
+// reference's input matrices (README.md:286-292).  gz_level < 0: plain text; else gzip members of 4096 rows at that level.
+extern "C" int epi_write_matrix_tsv(const char* path, const char* chrom, const int8_t* m, int64_t rows, int32_t cols,
+                                    int64_t pitch, int64_t bin_size, int64_t first_bin, int32_t gz_level, int32_t threads) {
+    EPI_REQUIRE(path && chrom && (m || rows == 0), "null pointer argument");
+    EPI_REQUIRE(rows >= 0 && cols >= 1 && pitch >= cols && bin_size >= 1, "bad shape");
+    if (gz_level > 9) gz_level = 9;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    const int64_t block = 4096;
+    const int64_t nblocks = (rows + block - 1) / block;
+    const size_t clen = strlen(chrom);
+    FILE* f = fopen(path, "wb");
+    EPI_REQUIRE(f != nullptr, "cannot open %s for writing", path);
+    // blocks are produced by a pool in waves of `threads * 4` and written in order, so that memory stays bounded
+    std::atomic<int> failed(0);
+    bool ok = true;
+    const int64_t wave = (int64_t)threads * 4;
+    std::vector<std::vector<unsigned char>> outs((size_t)wave);
+    for (int64_t w0 = 0; w0 < nblocks && ok && !failed; w0 += wave) {
+        const int64_t w1 = std::min(nblocks, w0 + wave);
+        std::atomic<int64_t> next(w0);
+        auto work = [&]() {
+            std::vector<char> text;
+            for (;;) {
+                const int64_t bi = next.fetch_add(1);
+                if (bi >= w1) break;
+                const int64_t lo = bi * block, hi = std::min(rows, lo + block);
+                text.resize((size_t)(hi - lo) * (clen + 48 + (size_t)cols * 4));
+                char* p = text.data();
+                for (int64_t r = lo; r < hi; ++r) {
+                    memcpy(p, chrom, clen);
+                    p += clen;
+                    *p++ = '\t';
+                    p = format_i64(p, (first_bin + r) * bin_size);
+                    *p++ = '\t';
+                    p = format_i64(p, (first_bin + r + 1) * bin_size);
+                    const int8_t* row = m + r * pitch;
+                    for (int32_t c = 0; c < cols; ++c) {
+                        const unsigned v = (unsigned)(row[c] + 1);          // 1 .. 128
+                        *p++ = '\t';
+                        if (v >= 100) *p++ = (char)('0' + v / 100);
+                        if (v >= 10) *p++ = (char)('0' + (v / 10) % 10);
+                        *p++ = (char)('0' + v % 10);
+                    }
+                    *p++ = '\n';
+                }
+                const size_t tlen = (size_t)(p - text.data());
+                std::vector<unsigned char>& o = outs[(size_t)(bi - w0)];
+                if (gz_level < 0) {
+                    o.assign(text.data(), text.data() + tlen);
+                    continue;
+                }
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (deflateInit2(&zs, gz_level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+                    failed = 1;
+                    break;
+                }
+                o.resize(deflateBound(&zs, (uLong)tlen) + 64);
+                zs.next_in = reinterpret_cast<Bytef*>(text.data());
+                zs.avail_in = (uInt)tlen;
+                zs.next_out = o.data();
+                zs.avail_out = (uInt)o.size();
+                const int rc = deflate(&zs, Z_FINISH);
+                o.resize(zs.total_out);
+                deflateEnd(&zs);
+                if (rc != Z_STREAM_END) {
+                    failed = 1;
+                    break;
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        const int nt = (int)std::min<int64_t>(threads, w1 - w0);
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+        for (int64_t bi = w0; bi < w1 && !failed; ++bi) {
+            std::vector<unsigned char>& o = outs[(size_t)(bi - w0)];
+            ok = ok && (fwrite(o.data(), 1, o.size(), f) == o.size());
+        }
+    }
+    if (nblocks == 0 && gz_level >= 0) {
+        static const unsigned char empty_gz[20] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        ok = fwrite(empty_gz, 1, sizeof(empty_gz), f) == sizeof(empty_gz);
+    }
+    ok = (fclose(f) == 0) && ok;
+    EPI_REQUIRE(!failed, "zlib deflate failed while writing %s", path);
+    EPI_REQUIRE(ok, "short write to %s", path);
+    return 0;
+}

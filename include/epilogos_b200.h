@@ -254,6 +254,16 @@ int epi_scores_tsv_close(void* handle);
 int epi_write_scores_gz(const char* path, const char* chrom_names, const int32_t* chrom_id, const int64_t* starts,
                         const int64_t* ends, const float* scores, int64_t rows, int32_t num_states, int32_t level,
                         int32_t threads);
+/* ChromHMM `-printstatebyline` files (one per biosample and chromosome: `<biosample> <chr>`, `MaxState E`, then one label per
+ * 200 bp bin) -> matrix: the native form of bin/preprocess_data_ChromHMM.sh:34-49, which pastes those files side by side.
+ * epi_statebyline_read  parses ONE file into a column: out[r * stride] = label - 1 for bin r (out == NULL: count only);
+ *                       *rows_out = bins in the file; chrom_out receives the chromosome named on the first line.
+ * epi_write_matrix_tsv  `chrom\tstart\tend\tlabel_1..label_C` per bin (labels 1-based, start = (first_bin + r) * bin_size):
+ *                       the text of the reference's input matrices (README.md:286-292); gz_level < 0 = plain text, else gzip. */
+int epi_statebyline_read(const char* path, int8_t* out, int64_t stride, int64_t cap_rows, int32_t num_states, int64_t* rows_out,
+                         char* chrom_out, int32_t chrom_cap);
+int epi_write_matrix_tsv(const char* path, const char* chrom, const int8_t* m, int64_t rows, int32_t cols, int64_t pitch,
+                         int64_t bin_size, int64_t first_bin, int32_t gz_level, int32_t threads);
 
 /* ---- region-of-interest selection over the per-bin score sums (host code) ---------------------------
  * helpers.maxMean (helpers.py:253-274) -> filter_regions maxmean (filter_regions.py:375-448): centered rolling
