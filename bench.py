@@ -93,22 +93,32 @@ def _reference_staged():
         return False
 
 
+def _write_sample(path, states0):
+    """One input matrix of the sample as TSV.gz (README.md:286-292).  The library's native writer when it loads (the
+    vectorised Python writer of the oracle takes ~10 s per 100,000 x 833 rows, all outside the timed region); same text."""
+    try:
+        from epilogos_b200 import preprocess
+        preprocess.write_matrix(path, "chr1", states0, gzip_level=1)
+    except Exception:
+        from oracle import reference_driver as ref
+        ref.write_matrix_tsv_gz(path, states0)
+
+
 def _sample_files(workdir, config, bins, cols, k, kind, seed=4242):
     """Write the TSV.gz sample of `bins` rows of the configuration; returns (file1, file2)."""
     from oracle import epilogos_oracle as orc
-    from oracle import reference_driver as ref
     workdir = Path(workdir)
     if config.startswith("paired"):
         a, b = workdir / "A", workdir / "B"
         a.mkdir(exist_ok=True)
         b.mkdir(exist_ok=True)
-        ref.write_matrix_tsv_gz(a / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 400, k, seed, kind))
-        ref.write_matrix_tsv_gz(b / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 433, k, seed + 1, kind))
+        _write_sample(a / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 400, k, seed, kind))
+        _write_sample(b / "epilogos_matrix_chr1.txt.gz", orc.synth_states(bins, 433, k, seed + 1, kind))
         return a / "epilogos_matrix_chr1.txt.gz", b / "epilogos_matrix_chr1.txt.gz"
     d = workdir / "in"
     d.mkdir(exist_ok=True)
     f = d / "epilogos_matrix_chr1.txt.gz"
-    ref.write_matrix_tsv_gz(f, orc.synth_states(bins, cols, k, seed, kind))
+    _write_sample(f, orc.synth_states(bins, cols, k, seed, kind))
     return f, "null"
 
 
