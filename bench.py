@@ -94,14 +94,19 @@ def _reference_staged():
 
 
 def _write_sample(path, states0):
-    """One input matrix of the sample as TSV.gz (README.md:286-292).  The library's native writer when it loads (the
-    vectorised Python writer of the oracle takes ~10 s per 100,000 x 833 rows, all outside the timed region); same text."""
-    try:
-        from epilogos_b200 import preprocess
-        preprocess.write_matrix(path, "chr1", states0, gzip_level=1)
-    except Exception:
-        from oracle import reference_driver as ref
-        ref.write_matrix_tsv_gz(path, states0)
+    """One input matrix of the sample as TSV.gz (README.md:286-292), outside every timed region.  Inside our own arm (the
+    `cpu_baseline` leg, where the library is loaded anyway) the library's native writer; in the `--impl reference` process
+    nothing of this repository's engine is loaded, so the oracle's vectorised Python writer (~10 s per 100,000 x 833 rows).
+    Same text either way."""
+    if "epilogos_b200._lib" in sys.modules:
+        try:
+            from epilogos_b200 import preprocess
+            preprocess.write_matrix(path, "chr1", states0, gzip_level=1)
+            return
+        except Exception:
+            pass
+    from oracle import reference_driver as ref
+    ref.write_matrix_tsv_gz(path, states0)
 
 
 def _sample_files(workdir, config, bins, cols, k, kind, seed=4242):
