@@ -1258,3 +1258,40 @@ extern "C" int epi_write_matrix_tsv(const char* path, const char* chrom, const i
     EPI_REQUIRE(ok, "short write to %s", path);
     return 0;
 }
+
+// columns src[c][0..rows) (contiguous, src_stride bytes apart) -> dst[r * pitch + c], c < cols: a group of columns of a pitched
+// matrix (dst may point at any column of it; bytes of a row outside [0, cols) are not touched).
+// Blocked so that both sides are touched a cache line at a time; row blocks over a few threads.
+extern "C" int epi_columns_to_rows(const int8_t* src, int64_t src_stride, int32_t cols, int64_t rows, int8_t* dst, int64_t pitch,
+                                   int32_t threads) {
+    EPI_REQUIRE((src && dst) || rows == 0 || cols == 0, "null pointer argument");
+    EPI_REQUIRE(cols >= 0 && rows >= 0 && pitch >= cols && src_stride >= rows, "bad shape");
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    constexpr int64_t RB = 256, CB = 64;
+    const int64_t nblocks = (rows + RB - 1) / RB;
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            const int64_t r0 = b * RB, r1 = std::min(rows, r0 + RB);
+            for (int64_t c0 = 0; c0 < cols; c0 += CB) {
+                const int64_t c1 = std::min<int64_t>(cols, c0 + CB);
+                for (int64_t r = r0; r < r1; ++r) {
+                    int8_t* d = dst + r * pitch;
+                    for (int64_t c = c0; c < c1; ++c) d[c] = src[c * src_stride + r];
+                }
+            }
+        }
+    };
+    const int nt = (int)std::min<int64_t>(threads, std::max<int64_t>(nblocks, 1));
+    if (nt <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+        for (auto& t : pool) t.join();
+    }
+    return 0;
+}

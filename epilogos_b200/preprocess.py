@@ -70,21 +70,29 @@ def read_chromosome(files, num_states=127, pinned=False, workers=None):
     bins, chrom = _read_column(files[0], 0, 1, 0, num_states)               # first file: count the bins
     pitch = helpers.pitch_for(len(files))
     buf = helpers._alloc_rows(bins, pitch, pinned)
-    buf[:, len(files):] = 0
     workers = workers or max(1, min(len(files), (os.cpu_count() or 2)))
-    base = buf.ctypes.data
+    # every file is parsed into a contiguous column (a byte per bin written 848 bytes apart straight into the matrix costs
+    # three times the parse), groups of columns are then turned into rows by a blocked transpose
+    group = 256
+    cols_buf = np.empty((min(group, len(files)), max(bins, 1)), dtype=np.int8)
+    names = []
 
-    def job(j):
-        rows, c = _read_column(files[j], base + j, pitch, bins, num_states)
+    def job(j, slot):
+        rows, c = _read_column(files[j], cols_buf.ctypes.data + slot * cols_buf.strides[0], 1, bins, num_states)
         if rows != bins:
             raise ValueError("%s holds %d bins, %s holds %d" % (files[j], rows, files[0], bins))
         return c
     _lib.call("epi_reader_concurrency", int(workers), 0)
     try:
         with ThreadPoolExecutor(max_workers=workers) as pool:
-            names = list(pool.map(job, range(len(files))))
+            for g0 in range(0, len(files), group):
+                g1 = min(len(files), g0 + group)
+                names += list(pool.map(job, range(g0, g1), range(g1 - g0)))
+                _lib.call("epi_columns_to_rows", ctypes.c_void_p(cols_buf.ctypes.data), int(cols_buf.strides[0]), g1 - g0, bins,
+                          ctypes.c_void_p(buf.ctypes.data + g0), pitch, 0)
     finally:
         _lib.call("epi_reader_concurrency", 0, 0)
+    buf[:, len(files):] = 0
     # awk takes the chromosome from the first pasted line, i.e. from the first file (preprocess_data_ChromHMM.sh:47)
     return buf[:, :len(files)], names[0] if names else chrom
 

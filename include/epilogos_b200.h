@@ -264,6 +264,11 @@ int epi_statebyline_read(const char* path, int8_t* out, int64_t stride, int64_t 
                          char* chrom_out, int32_t chrom_cap);
 int epi_write_matrix_tsv(const char* path, const char* chrom, const int8_t* m, int64_t rows, int32_t cols, int64_t pitch,
                          int64_t bin_size, int64_t first_bin, int32_t gz_level, int32_t threads);
+/* columns src[c][0..rows) (src_stride bytes apart) -> dst[r * pitch + c], c < cols (dst may point at any column of a pitched
+ * int8 matrix; other bytes of a row are not touched): the per-biosample columns of epi_statebyline_read, read contiguously,
+ * into the layout the kernels consume. */
+int epi_columns_to_rows(const int8_t* src, int64_t src_stride, int32_t cols, int64_t rows, int8_t* dst, int64_t pitch,
+                        int32_t threads);
 
 /* ---- region-of-interest selection over the per-bin score sums (host code) ---------------------------
  * helpers.maxMean (helpers.py:253-274) -> filter_regions maxmean (filter_regions.py:375-448): centered rolling

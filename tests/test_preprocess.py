@@ -81,6 +81,24 @@ def test_matrices_equal_the_scripts_recipe(tmp_path):
             assert (ref / ("matrix_%s.txt" % chrom)).read_bytes() == (tmp_path / "out" / ("matrix_%s.txt" % chrom)).read_bytes()
 
 
+def test_more_biosamples_than_one_column_group(tmp_path):
+    """Columns are parsed contiguously and turned into rows in groups of 256: 300 biosamples cross a group boundary."""
+    rng = np.random.default_rng(43)
+    data = tmp_path / "calls"
+    data.mkdir()
+    n, bins = 300, 53
+    x = rng.integers(1, 16, size=(bins, n))
+    (tmp_path / "meta.tsv").write_text("id\n" + "".join("S%04d\n" % j for j in range(n)))
+    (tmp_path / "sizes.genome").write_text("chr21\t48129895\n")
+    for j in range(n):
+        _statebyline(data / ("S%04d_15_chr21_statebyline.txt" % j), "S%04d" % j, "chr21", x[:, j], gz=False)
+    files = preprocess.find_files(data, preprocess.biosamples(tmp_path / "meta.tsv"), "chr21")
+    m, chrom = preprocess.read_chromosome(files, num_states=15)
+    assert chrom == "chr21" and np.array_equal(m, x - 1) and not m.base[:, n:].any()
+    preprocess.main(data, tmp_path / "meta.tsv", tmp_path / "sizes.genome", tmp_path / "out", out=io.StringIO())
+    assert (tmp_path / "out" / "matrix_chr21.txt").read_text() == _paste_awk([x[:, j] for j in range(n)], "chr21")
+
+
 def test_bad_inputs_are_errors(tmp_path):
     data = tmp_path / "calls"
     data.mkdir()
