@@ -68,3 +68,20 @@ def test_product_never_imports_the_oracle():
     for f in pkg.rglob("*.py"):
         text = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header compiles as C99 and as C++11 with warnings as errors (plain pointers and
+    sizes only, nothing from torch or CUDA in a signature)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    for cc, std, name in (("gcc", "-std=c99", "h.c"), ("g++", "-std=c++11", "h.cpp")):
+        src = tmp_path / name
+        src.write_text('#include "epilogos_b200.h"\nint main(void) { return epi_abi_version == 0; }\n')
+        r = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = (ROOT / "include" / "epilogos_b200.h").read_text()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", text, flags=re.S) and "#include <cuda" not in text
