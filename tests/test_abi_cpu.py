@@ -79,7 +79,7 @@ def test_header_is_plain_c(tmp_path):
         pytest.skip("no host compiler")
     for cc, std, name in (("gcc", "-std=c99", "h.c"), ("g++", "-std=c++11", "h.cpp")):
         src = tmp_path / name
-        src.write_text('#include "epilogos_b200.h"\nint main(void) { return epi_abi_version == 0; }\n')
+        src.write_text('#include "epilogos_b200.h"\nint main(void) { return epi_abi_version() == EPI_ABI_VERSION ? 0 : 1; }\n')
         r = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), str(src)],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
