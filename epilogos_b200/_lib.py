@@ -56,6 +56,7 @@ PROTOTYPES = {
     "epi_inflate_file": (c_int, [c_char_p, c_void_p, c_int64, POINTER(c_int64)]),
     "epi_reader_stats": (c_int, [POINTER(c_int64)]),
     "epi_reader_concurrency": (c_int, [c_int32, c_int32]),
+    "epi_reader_threads": (c_int, [POINTER(c_int32), POINTER(c_int32)]),
     "epi_statebyline_read": (c_int, [c_char_p, c_void_p, c_int64, c_int64, c_int32, POINTER(c_int64), c_char_p, c_int32]),
     "epi_columns_to_rows": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64, c_int32]),
     "epi_write_matrix_tsv": (c_int, [c_char_p, c_char_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_int64, c_int32,

@@ -57,6 +57,9 @@ static int cores_per_reader() {
 }
 // what the calling thread's last reader did (epi_reader_stats): mode, chunks, chunks with a start, chunks accepted
 static thread_local int64_t t_reader_stats[4] = {0, 0, 0, 0};
+}  // namespace epi
+static int parse_threads();
+namespace epi {
 // threads that decode ONE gzip stream in parallel (parallel_inflate.h); 1 = the sequential decoder
 static int inflate_threads() {
     if (const char* e = getenv("EPI_INFLATE_THREADS")) {
@@ -664,6 +667,12 @@ extern "C" int epi_inflate_file(const char* path, uint8_t* out, int64_t cap, int
 extern "C" int epi_reader_concurrency(int32_t files, int32_t ranks) {
     g_expected_readers.store(files > 0 ? files : 0);
     g_reading_ranks.store(ranks > 0 ? ranks : 0);
+    return 0;
+}
+
+extern "C" int epi_reader_threads(int32_t* inflate_out, int32_t* parse_out) {
+    if (inflate_out) *inflate_out = inflate_threads();
+    if (parse_out) *parse_out = parse_threads();
     return 0;
 }
 

@@ -232,6 +232,8 @@ int epi_reader_stats(int64_t* out4);
  * read at the same time (0: all LOCAL_WORLD_SIZE of them; 1 when one rank reads for everybody): every reader then takes
  * its share of the cores for its inflate and parser threads from the start.  (0, 0) clears the hint. */
 int epi_reader_concurrency(int32_t files, int32_t ranks);
+/* Diagnostic: the threads a reader opened now would use for its gzip stream (1 = sequential decoder) and for row parsing. */
+int epi_reader_threads(int32_t* inflate_out, int32_t* parse_out);
 int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out);
 int epi_tsv_parse_open(const char* path, int32_t num_states, void** handle_out, int64_t* rows_out, int32_t* cols_out,
                        int32_t* n_chrom_out, int32_t* names_bytes_out);

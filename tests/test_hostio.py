@@ -239,6 +239,42 @@ def test_parser_fast_and_careful_paths_agree(tmp_path):
             helpers.read_matrix(p, num_states=18)
 
 
+def test_reader_thread_budget_divides_the_host(monkeypatch):
+    """A reader takes its share of the cores: all of them alone, 1/N under torchrun with N ranks on the host
+    (LOCAL_WORLD_SIZE), 1/files when session.prefetch announces that many concurrent reads, the whole host again when one
+    rank reads for everybody; three quarters of the share inflate, a third parses; the knobs override."""
+    import ctypes
+    import os
+    from epilogos_b200 import _lib
+
+    def budget():
+        a, b = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.call("epi_reader_threads", ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+    for name in ("EPI_INFLATE_THREADS", "EPI_PARSE_THREADS", "LOCAL_WORLD_SIZE"):
+        monkeypatch.delenv(name, raising=False)
+    cores = len(os.sched_getaffinity(0))
+    alone = budget()
+    want_inflate = min(12, (cores * 3 + 2) // 4)
+    assert alone == (want_inflate if want_inflate >= 2 else 1, max(1, min(8, (cores + 2) // 3)))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", str(cores))               # one core per rank: the sequential decoder, one parser
+    assert budget() == (1, 1)
+    _lib.call("epi_reader_concurrency", 1, 1)                        # ... unless one rank reads for everybody
+    try:
+        assert budget() == alone
+    finally:
+        _lib.call("epi_reader_concurrency", 0, 0)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE")
+    _lib.call("epi_reader_concurrency", cores, 0)                    # as many files at once as there are cores
+    try:
+        assert budget() == (1, 1)
+    finally:
+        _lib.call("epi_reader_concurrency", 0, 0)
+    monkeypatch.setenv("EPI_INFLATE_THREADS", "5")
+    monkeypatch.setenv("EPI_PARSE_THREADS", "7")
+    assert budget() == (5, 7)
+
+
 def test_gzip_trailer_crc_is_checked_by_both_crc_paths(tmp_path, monkeypatch):
     """The CRC-32 of the trailer check runs on carry-less multiplies where the CPU has them (csrc/crc_clmul.cpp) and on zlib's
     tables otherwise and for short pieces: members of every length around the 64-byte folding width and the 256-byte
