@@ -72,41 +72,6 @@ static int inflate_threads() {
     return t < 2 ? 1 : t;
 }
 
-struct Reader {
-    gzFile gz = nullptr;       // gzopen reads plain files transparently as well
-    std::vector<char> buf;
-    size_t pos = 0, len = 0;
-    bool eof = false;
-
-    bool open(const char* path) {
-        gz = gzopen(path, "rb");
-        if (!gz) return false;
-        gzbuffer(gz, 1 << 20);
-        buf.resize(8 << 20);
-        return true;
-    }
-    bool fill() {
-        if (eof) return false;
-        const int n = gzread(gz, buf.data(), (unsigned)buf.size());
-        if (n <= 0) {
-            eof = true;
-            len = pos = 0;
-            return false;
-        }
-        len = (size_t)n;
-        pos = 0;
-        return true;
-    }
-    // next byte or -1
-    inline int get() {
-        if (pos == len && !fill()) return -1;
-        return (unsigned char)buf[pos++];
-    }
-    ~Reader() {
-        if (gz) gzclose(gz);
-    }
-};
-
 // "%.5f" of a double with printf semantics (round-half-even on the exact binary value).  Fast path: scale by 1e5 and
 // round; whenever the scaled value is within 1e-6 of a rounding boundary (or huge / non-finite) defer to snprintf.
 static inline char* format_5f(char* p, double d) {
@@ -157,33 +122,6 @@ static inline char* format_i64(char* p, long long v) {
 }  // namespace epi
 
 using namespace epi;
-
-extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out) {
-    EPI_REQUIRE(path != nullptr, "null path");
-    Reader rd;
-    EPI_REQUIRE(rd.open(path), "cannot open %s", path);
-    int64_t rows = 0;
-    int32_t tabs_first = 0;
-    bool first = true;
-    while (rd.fill()) {
-        const char* b = rd.buf.data();
-        const size_t n = rd.len;
-        size_t i = 0;
-        if (first) {
-            for (; i < n; ++i) {
-                if (b[i] == '\t') ++tabs_first;
-                else if (b[i] == '\n') {
-                    first = false;
-                    break;
-                }
-            }
-        }
-        for (; i < n; ++i) rows += (b[i] == '\n');
-    }
-    if (rows_out) *rows_out = rows;
-    if (cols_out) *cols_out = tabs_first + 1 - 3;           // biosample columns (after chr, start, end)
-    return 0;
-}
 
 // Line source: a background thread inflates the file into a ring of two large blocks while the caller parses the
 // previous one; lines that straddle a block boundary are stitched into a side buffer.  The two threads hand blocks over
@@ -540,6 +478,41 @@ struct LineSource {
         }
     }
 };
+
+extern "C" int epi_tsv_shape(const char* path, int64_t* rows_out, int32_t* cols_out) {
+    EPI_REQUIRE(path != nullptr, "null path");
+    LineSource src;                                       // the library's decoders (several threads on a large file)
+    EPI_REQUIRE(src.open(path), "cannot open %s", path);
+    int64_t rows = 0;
+    int32_t tabs_first = 0;
+    bool first = true;
+    const char* b;
+    size_t n;
+    while (src.next_raw(b, n)) {
+        size_t i = 0;
+        if (first) {
+            for (; i < n; ++i) {
+                if (b[i] == '\t') ++tabs_first;
+                else if (b[i] == '\n') {
+                    first = false;
+                    break;
+                }
+            }
+        }
+        const char* p = b + i;
+        const char* const e = b + n;
+        while (p < e) {                                   // newline count as in helpers.countRows (helpers.py:92-97)
+            const char* q = static_cast<const char*>(memchr(p, '\n', (size_t)(e - p)));
+            if (q == nullptr) break;
+            ++rows;
+            p = q + 1;
+        }
+    }
+    EPI_REQUIRE(src.error().empty(), "%s", src.error().c_str());
+    if (rows_out) *rows_out = rows;
+    if (cols_out) *cols_out = tabs_first + 1 - 3;           // biosample columns (after chr, start, end)
+    return 0;
+}
 
 // One row `chr \t start \t end \t s_1 .. s_C` -> labels-1 in dst[0..cols), coordinates, chromosome id (names grows).
 // Returns 0, or 2 with the error set.
